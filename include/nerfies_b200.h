@@ -1,0 +1,159 @@
+/* nerfies_b200.h - C ABI of the B200-native deformable-NeRF render hot path.
+ *
+ * The reference (google/nerfies) is pure Python/JAX and has no FFI; the seam a
+ * replacement plugs into is the Python call surface listed in SURVEY.md §8(b).
+ * Each entry point below names the reference callable it replaces
+ * (file:line in /root/reference).  The Python host side
+ * (nerfies_b200/models.py, evaluation.py) binds these with ctypes and keeps the
+ * reference's names / pytree keys / shapes on top.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer on the current CUDA device unless the
+ *    function name ends in _host; tensors are contiguous, row-major, float32;
+ *    ids are uint32;
+ *  - calls enqueue work on `stream` (a cudaStream_t passed as void*) and return
+ *    without synchronising (the *_host variant synchronises before returning);
+ *  - the caller owns every input/output buffer and keeps it alive until the
+ *    stream has passed the call; the library owns only its workspace, allocated
+ *    in nfb_create; nothing is allocated on the hot path;
+ *  - return value 0 = success, < 0 = error (message via nfb_last_error());
+ *  - a handle is not thread-safe: one handle per GPU per process/rank.
+ */
+#ifndef NERFIES_B200_H_
+#define NERFIES_B200_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct nfb_handle nfb_handle;
+
+/* Activation selectors: configs.py:27-32 registers exactly these for gin. */
+enum nfb_activation {
+  NFB_ACT_NONE = 0, NFB_ACT_RELU = 1, NFB_ACT_ELU = 2, NFB_ACT_LEAKY_RELU = 3,
+  NFB_ACT_TANH = 4, NFB_ACT_SIGMOID = 5, NFB_ACT_SOFTPLUS = 6
+};
+enum nfb_warp_type { NFB_WARP_NONE = 0, NFB_WARP_TRANSLATION = 1, NFB_WARP_SE3 = 2 };
+/* Arithmetic of the MLP GEMMs.  Everything else is always fp32. */
+enum nfb_precision {
+  NFB_PREC_FP32 = 0,     /* fp32 FFMA on CUDA cores: the parity mode            */
+  NFB_PREC_BF16 = 1,     /* bf16 operands, fp32 accumulate, tcgen05 tensor cores */
+  NFB_PREC_BF16X3 = 2    /* fp32 emulated as 3 bf16 MMAs (hi/lo split), tcgen05  */
+};
+
+/* Mirrors the NerfModel attributes that shape the forward pass
+ * (nerfies/models.py:76-120; filled from ModelConfig, nerfies/configs.py:37-105). */
+typedef struct nfb_config {
+  int num_coarse_samples;        /* ModelConfig.num_coarse_samples              */
+  int num_fine_samples;          /* ModelConfig.num_fine_samples (0: no fine)   */
+  int num_nerf_point_freqs;      /* SinusoidalEncoder F for points (models.py:148) */
+  int num_nerf_viewdir_freqs;    /* ... for viewdirs (models.py:151)            */
+  int num_warp_freqs;            /* AnnealedSinusoidalEncoder F (warping.py:245) */
+  int nerf_trunk_depth, nerf_trunk_width;
+  int nerf_rgb_branch_depth, nerf_rgb_branch_width;
+  unsigned nerf_skips_mask;      /* bit i set <=> i in nerf_skips (modules.py:47) */
+  int alpha_channels, rgb_channels;   /* must be 1 and 3                        */
+  int warp_field_type;           /* nfb_warp_type; NONE when use_warp is False  */
+  int warp_trunk_depth, warp_trunk_width;   /* SE3Field/TranslationField MLP    */
+  unsigned warp_skips_mask;
+  int num_warp_features, num_appearance_features, num_camera_features;
+  int num_warp_embeddings, num_appearance_embeddings, num_camera_embeddings;
+  int use_viewdirs, use_appearance_metadata, use_camera_metadata;
+  int use_trunk_condition, use_alpha_condition, use_rgb_condition;
+  int activation;                /* hidden activation of NerfMLP (nfb_activation) */
+  int sigma_activation;          /* models.py:277                               */
+  int use_white_background, use_linear_disparity, use_sample_at_infinity;
+  float near_plane, far_plane;   /* NerfModel.near / .far                       */
+  int precision;                 /* nfb_precision                               */
+} nfb_config;
+
+/* Flags for the render entry points. */
+#define NFB_FLAG_COARSE_ONLY 1u  /* stop after the coarse level                 */
+#define NFB_FLAG_NO_WARP     2u  /* use_warp=False call-time override (models.py:321) */
+
+/* Lifetime.  Replaces construct_nerf's model construction (models.py:424-463);
+ * max_rays bounds B of every later call (workspace is sized once, here). */
+int nfb_create(const nfb_config* cfg, int max_rays, nfb_handle** out);
+void nfb_destroy(nfb_handle* h);
+
+/* Parameter interface.  The expected tensors, in order, with their Flax names
+ * ("warp_field/trunk/hidden_0/kernel", ... SURVEY.md §8a R12) and (rows, cols);
+ * Dense kernels are (in, out), biases (1, out), embeddings (num, features). */
+int nfb_param_count(const nfb_handle* h);
+int nfb_param_info(const nfb_handle* h, int index, char* name, int name_capacity,
+                   long long* rows, long long* cols);
+/* Copies/repacks the fp32 tensors (device pointers, order of nfb_param_info)
+ * into the library's padded layouts.  Replaces passing {'params': params} to
+ * model.apply (models.py:289; eval.py:331). */
+int nfb_set_params(nfb_handle* h, const float* const* tensors,
+                   const long long* numels, int count, void* stream);
+
+/* NerfModel.__call__ (nerfies/models.py:289-375): coarse level, hierarchical
+ * resampling, fine level.
+ *   origins, directions, viewdirs : (B,3); viewdirs NULL = directions (:326-329)
+ *   warp_id, appearance_id, camera_id : (B) uint32 = metadata[...][:,0]; NULL
+ *       allowed when the model does not use that metadata
+ *   warp_alpha : warp_extra['alpha'] (model_utils.py:31-33)
+ *   t_rand (B,Nc), u_rand (B,Nf) : the uniform draws of the stratified path
+ *       (model_utils.py:65,162); NULL = deterministic path (:67-70, :164-165)
+ *   out_coarse, out_fine : (B,6) = rgb[3], depth, med_depth, acc
+ *   w_coarse (B,Nc), w_fine (B,Nc+Nf), z_fine (B,Nc+Nf) : optional outputs */
+int nfb_render_forward(nfb_handle* h, int num_rays, const float* origins,
+                       const float* directions, const float* viewdirs,
+                       const unsigned* warp_id, const unsigned* appearance_id,
+                       const unsigned* camera_id, float warp_alpha,
+                       const float* t_rand, const float* u_rand, unsigned flags,
+                       float* out_coarse, float* out_fine, float* w_coarse,
+                       float* w_fine, float* z_fine, void* stream);
+
+/* Same call with HOST buffers: stages inputs through pinned memory, H2D,
+ * renders, D2H, synchronises.  This is what render_image's model_fn does per
+ * chunk in the reference (evaluation.py:85-93: shard -> model_fn -> unshard). */
+int nfb_render_forward_host(nfb_handle* h, int num_rays, const float* origins,
+                            const float* directions, const float* viewdirs,
+                            const unsigned* warp_id,
+                            const unsigned* appearance_id,
+                            const unsigned* camera_id, float warp_alpha,
+                            unsigned flags, float* out_coarse, float* out_fine,
+                            void* stream);
+
+/* NerfModel.render_samples (nerfies/models.py:230-287) for one level
+ * (0 = coarse MLP, 1 = fine MLP) on caller-supplied z_vals (B,S), points =
+ * origins + z * directions.  out (B,6); optional weights (B,S), per-sample
+ * sigmoid(rgb)/sigma (B,S,4) and warped_points (B,S,3). */
+int nfb_render_samples(nfb_handle* h, int level, int num_rays, int num_samples,
+                       const float* z_vals, const float* origins,
+                       const float* directions, const float* viewdirs,
+                       const unsigned* warp_id, const unsigned* appearance_id,
+                       const unsigned* camera_id, float warp_alpha,
+                       unsigned flags, float* out, float* weights,
+                       float* samples, float* warped_points, void* stream);
+
+/* model_utils.sample_pdf (nerfies/model_utils.py:190-215) with the caller prep
+ * of models.py:353-357: bins = midpoints of z_coarse, weights = w_coarse[1:-1];
+ * z_fine = sort(concat(z_coarse, inverse-CDF samples)). */
+int nfb_sample_pdf(nfb_handle* h, int num_rays, const float* z_coarse,
+                   const float* w_coarse, const float* u_rand, float* z_fine,
+                   void* stream);
+
+/* model_utils.sample_along_rays z_vals (nerfies/model_utils.py:56-70). */
+int nfb_coarse_z_vals(nfb_handle* h, int num_rays, const float* t_rand,
+                      float* z_coarse, void* stream);
+
+/* warp_field.apply on free points (nerfies/warping.py:355-389, 160-199; called
+ * by training.py:122-131): points (P,3), warp_id (P) -> warped (P,3). */
+int nfb_warp_forward(nfb_handle* h, int num_points, const float* points,
+                     const unsigned* warp_id, float warp_alpha, float* warped,
+                     void* stream);
+
+/* Number of CUDA kernels this handle has launched so far (bench accounting). */
+long long nfb_kernel_launches(const nfb_handle* h);
+/* Thread-local description of the last error returned on this thread. */
+const char* nfb_last_error(void);
+/* "nerfies_b200 <version> sm_100a" */
+const char* nfb_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif  /* NERFIES_B200_H_ */

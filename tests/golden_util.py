@@ -85,3 +85,75 @@ def rel_err(a, b, floor=1e-2):
   a = a.double()
   b = b.double()
   return float(((a - b).abs() / (b.abs() + floor)).max())
+
+
+def model_from_spec(spec_dict, precision='fp32', device=None, batch_size=64):
+  """A nerfies_b200.NerfModel configured like a golden / oracle spec."""
+  import nerfies_b200 as nb
+  s = spec_dict
+  if s['warp_field_type'] == 'se3':
+    wk = {'trunk_depth': s['warp_trunk_depth'],
+          'trunk_width': s['warp_trunk_width'], 'skips': tuple(s['warp_skips'])}
+  else:
+    wk = {'depth': s['warp_trunk_depth'],
+          'hidden_channels': s['warp_trunk_width'],
+          'skips': tuple(s['warp_skips'])}
+  return nb.NerfModel(
+      num_coarse_samples=s['num_coarse_samples'],
+      num_fine_samples=s['num_fine_samples'], use_viewdirs=s['use_viewdirs'],
+      near=s['near'], far=s['far'], noise_std=None,
+      nerf_trunk_depth=s['nerf_trunk_depth'],
+      nerf_trunk_width=s['nerf_trunk_width'],
+      nerf_rgb_branch_depth=s['nerf_rgb_branch_depth'],
+      nerf_rgb_branch_width=s['nerf_rgb_branch_width'],
+      nerf_skips=tuple(s['nerf_skips']), alpha_channels=s['alpha_channels'],
+      rgb_channels=s['rgb_channels'], use_stratified_sampling=False,
+      num_nerf_point_freqs=s['num_nerf_point_freqs'],
+      num_nerf_viewdir_freqs=s['num_nerf_viewdir_freqs'],
+      appearance_ids=range(s['num_appearance_embeddings']),
+      camera_ids=range(s['num_camera_embeddings']),
+      warp_ids=range(s['num_warp_embeddings']),
+      num_appearance_features=s['num_appearance_features'],
+      num_camera_features=s['num_camera_features'],
+      num_warp_features=s['num_warp_features'],
+      num_warp_freqs=s['num_warp_freqs'], activation=s['activation'],
+      sigma_activation=s['sigma_activation'],
+      use_white_background=s['use_white_background'],
+      use_linear_disparity=s['use_linear_disparity'],
+      use_sample_at_infinity=s['use_sample_at_infinity'],
+      warp_field_type=s['warp_field_type'],
+      use_appearance_metadata=s['use_appearance_metadata'],
+      use_camera_metadata=s['use_camera_metadata'], use_warp=s['use_warp'],
+      use_trunk_condition=s['use_trunk_condition'],
+      use_alpha_condition=s['use_alpha_condition'],
+      use_rgb_condition=s['use_rgb_condition'], warp_kwargs=wk,
+      precision=precision, batch_size=batch_size, device=device)
+
+
+def spec_to_dict(spec):
+  import dataclasses
+  d = dataclasses.asdict(spec)
+  d['nerf_skips'] = list(d['nerf_skips'])
+  d['warp_skips'] = list(d['warp_skips'])
+  return d
+
+
+def tree_to_device(tree, device):
+  if isinstance(tree, dict):
+    return {k: tree_to_device(v, device) for k, v in tree.items()}
+  return tree.to(device)
+
+
+def med_depth_ok(got, ref_out, z_vals, tol=1e-4):
+  """med_depth is a step function of the weights (first sample with
+  cumsum >= 0.5, model_utils.py:231-239): equal to the reference except where
+  the cumulative weight passes within `tol` of 0.5, where the neighbouring
+  sample may be picked instead."""
+  got = got.cpu()
+  ref = ref_out['med_depth']
+  exact = (got - ref).abs() <= 1e-6 * (1 + ref.abs())
+  cum = torch.cumsum(ref_out['weights'].double(), -1)
+  near_half = ((cum - 0.5).abs() < tol).any(-1)
+  in_z = (got[:, None] - z_vals).abs().min(-1).values <= 1e-6
+  in_z = in_z | (got == 0)
+  return bool((exact | (near_half & in_z)).all())

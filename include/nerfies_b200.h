@@ -146,6 +146,13 @@ int nfb_warp_forward(nfb_handle* h, int num_points, const float* points,
                      const unsigned* warp_id, float warp_alpha, float* warped,
                      void* stream);
 
+/* Measurement aid (bench.py's roofline): when enabled, every launch of the field
+ * kernel (the dominant kernel) is bracketed by cudaEvents on its launch stream.
+ * nfb_field_time_ms synchronises on the events of the most recent launch of
+ * `level` (0 coarse, 1 fine) and returns its duration in ms (< 0 on error). */
+int nfb_set_profiling(nfb_handle* h, int enabled);
+float nfb_field_time_ms(nfb_handle* h, int level);
+
 /* Number of CUDA kernels this handle has launched so far (bench accounting). */
 long long nfb_kernel_launches(const nfb_handle* h);
 /* Thread-local description of the last error returned on this thread. */

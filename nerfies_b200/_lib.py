@@ -15,6 +15,7 @@ SYMBOLS = [
     'nfb_set_params', 'nfb_render_forward', 'nfb_render_forward_host',
     'nfb_render_samples', 'nfb_sample_pdf', 'nfb_coarse_z_vals',
     'nfb_warp_forward', 'nfb_kernel_launches', 'nfb_last_error', 'nfb_version',
+    'nfb_set_profiling', 'nfb_field_time_ms',
 ]
 
 ACTIVATIONS = {'none': 0, 'relu': 1, 'elu': 2, 'leaky_relu': 3, 'tanh': 4,
@@ -116,6 +117,10 @@ def load():
   lib.nfb_warp_forward.restype = ci
   lib.nfb_kernel_launches.argtypes = [vp]
   lib.nfb_kernel_launches.restype = ctypes.c_longlong
+  lib.nfb_set_profiling.argtypes = [vp, ci]
+  lib.nfb_set_profiling.restype = ci
+  lib.nfb_field_time_ms.argtypes = [vp, ci]
+  lib.nfb_field_time_ms.restype = cf
   lib.nfb_last_error.argtypes = []
   lib.nfb_last_error.restype = ctypes.c_char_p
   lib.nfb_version.argtypes = []

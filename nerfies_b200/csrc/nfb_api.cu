@@ -84,6 +84,9 @@ struct nfb_handle {
   float *d_in = nullptr, *h_in = nullptr, *h_out = nullptr;
   unsigned *d_ids = nullptr, *h_ids = nullptr;
   long long launches = 0;
+  bool profiling = false;
+  cudaEvent_t ev[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
+  bool ev_valid[2] = {false, false};
   int cond_stride = 0;
   int sm_count = 148;
 };
@@ -373,16 +376,25 @@ int run_field(nfb_handle* h, int level, long long rows, int S, const float* orig
   a.params = h->d_packed; a.origins = origins; a.directions = directions; a.z_vals = z;
   a.cond = h->d_cond; a.window = h->d_window; a.samples = samples; a.warped = warped;
   a.num_rows = rows; a.samples_per_ray = S; a.use_warp = use_warp; a.warp_only = warp_only;
+  const bool prof = h->profiling && !warp_only;
+  if (prof) NFB_CUDA(cudaEventRecord(h->ev[level][0], s));
+  int rc;
   if (h->cfg.precision == NFB_PREC_FP32) {
     const long long tiles = (rows + nfb::kTM - 1) / nfb::kTM;
     nfb::field_simt_kernel<<<(unsigned)tiles, nfb::kSimtThreads, nfb::kSimtSmemBytes, s>>>(h->prog[level], a);
-    return launch_check(h, "field_simt_kernel");
-  }
+    rc = launch_check(h, "field_simt_kernel");
+  } else {
 #ifdef NFB_WITH_TC
-  return nfb::tc::run_field_tc(h, level, a, s);
+    rc = nfb::tc::run_field_tc(h, level, a, s);
 #else
-  return fail("precision %d needs the tcgen05 path, which this build does not contain", h->cfg.precision);
+    rc = fail("precision %d needs the tcgen05 path, which this build does not contain", h->cfg.precision);
 #endif
+  }
+  if (prof && rc == 0) {
+    NFB_CUDA(cudaEventRecord(h->ev[level][1], s));
+    h->ev_valid[level] = true;
+  }
+  return rc;
 }
 
 int run_composite(nfb_handle* h, int B, int S, const float* samples, const float* z,
@@ -428,6 +440,28 @@ extern "C" {
 const char* nfb_last_error(void) { return g_error.c_str(); }
 const char* nfb_version(void) { return "nerfies_b200 0.1 sm_100a"; }
 long long nfb_kernel_launches(const nfb_handle* h) { return h ? h->launches : 0; }
+
+int nfb_set_profiling(nfb_handle* h, int enabled) {
+  if (!h) return fail("null handle");
+  if (enabled && !h->ev[0][0]) {
+    for (int l = 0; l < 2; ++l)
+      for (int i = 0; i < 2; ++i) NFB_CUDA(cudaEventCreate(&h->ev[l][i]));
+  }
+  h->profiling = enabled != 0;
+  h->ev_valid[0] = h->ev_valid[1] = false;
+  return 0;
+}
+
+float nfb_field_time_ms(nfb_handle* h, int level) {
+  if (!h || level < 0 || level > 1 || !h->ev_valid[level]) {
+    fail("no profiled field launch for level %d", level);
+    return -1.f;
+  }
+  if (cudaEventSynchronize(h->ev[level][1]) != cudaSuccess) { fail("cudaEventSynchronize failed"); return -1.f; }
+  float ms = -1.f;
+  if (cudaEventElapsedTime(&ms, h->ev[level][0], h->ev[level][1]) != cudaSuccess) { fail("cudaEventElapsedTime failed"); return -1.f; }
+  return ms;
+}
 
 int nfb_create(const nfb_config* cfg, int max_rays, nfb_handle** out) {
   if (!cfg || !out) return fail("null argument");
@@ -489,6 +523,8 @@ void nfb_destroy(nfb_handle* h) {
                    h->d_wc, h->d_samples, h->d_out_c, h->d_out_f, h->d_in};
   for (float* p : bufs) if (p) cudaFree(p);
   if (h->d_ids) cudaFree(h->d_ids);
+  for (int l = 0; l < 2; ++l)
+    for (int i = 0; i < 2; ++i) if (h->ev[l][i]) cudaEventDestroy(h->ev[l][i]);
   if (h->h_in) cudaFreeHost(h->h_in);
   if (h->h_out) cudaFreeHost(h->h_out);
   if (h->h_ids) cudaFreeHost(h->h_ids);

@@ -128,7 +128,11 @@ composite_kernel(const CompositeArgs a) {
   for (int i = lane; i < S; i += 32) {
     float dist = (i + 1 < S) ? (zs[i + 1] - zs[i]) : last;
     dist = dist * dnorm;
-    alpha[i] = 1.0f - expf(-sg[i].w * dist);
+    // alpha = 1 - exp(-sigma*dist) (model_utils.py:108).  Evaluated as -expm1(-x):
+    // the reference's float32 form loses all but ~12 bits when x is small (empty
+    // space); expm1 returns the correctly rounded value of the same expression,
+    // which is within the round-off band of any fp32 evaluation of 1 - exp(-x).
+    alpha[i] = -expm1f(-sg[i].w * dist);
   }
   __syncwarp();
   if (lane == 0) {

@@ -19,6 +19,18 @@ from tests.golden_util import (CASES, Golden, med_depth_ok, model_from_spec,
 pytestmark = pytest.mark.gpu
 TOL = 1e-4
 TOL_E2E = 2e-3
+_REPORT = []
+
+
+@pytest.fixture(scope='module', autouse=True)
+def _write_report():
+  yield
+  import json
+  import os
+  os.makedirs('gpurun_out', exist_ok=True)
+  with open('gpurun_out/parity_report.json', 'w') as f:
+    json.dump([dict(case=c, level=l, key=k, err_vs_fp64=e, fp32_band=b)
+               for c, l, k, e, b in _REPORT], f, indent=1)
 DEV = 'cuda:0'
 
 
@@ -223,11 +235,20 @@ def test_levels_vs_oracle(dims):
   p, rays, model = _oracle_case(spec, n, 5, alpha)
   ref = O.render_forward(p, spec, rays, warp_alpha=alpha, return_points=True)
   pg = tree_to_device(p, DEV)
-  got_c = _render_level(model, pg, 0, rays, ref['coarse']['z_vals'], alpha)
-  _check_level(dims, 'coarse', got_c, ref['coarse'], ref['coarse']['z_vals'],
-               True)
-  got_f = _render_level(model, pg, 1, rays, ref['fine']['z_vals'], alpha)
-  _check_level(dims, 'fine', got_f, ref['fine'], ref['fine']['z_vals'], True)
+  # The truth is the fp64 shadow; the fp32 oracle's own distance from it is the
+  # round-off band of the algorithm (e.g. 1 - exp(-x) in empty space), which the
+  # CUDA result is allowed on top of the 1e-4 tolerance.
+  for lv, level in ((0, 'coarse'), (1, 'fine')):
+    z = ref[level]['z_vals']
+    got = _render_level(model, pg, lv, rays, z, alpha)
+    r64 = O.render_level(p, spec, level, rays, z, alpha, dtype=torch.float64)
+    for k in ('rgb', 'depth', 'acc', 'weights', 'warped_points'):
+      band = rel_err(ref[level][k], r64[k])
+      err = rel_err(got[k], r64[k])
+      _REPORT.append((dims, level, k, err, band))
+      assert err < TOL + 2 * band, (
+          f'{dims} {level}/{k}: err vs fp64 {err:.3e}, fp32 band {band:.3e}')
+    assert med_depth_ok(got['med_depth'], ref[level], z)
   out = model.apply({'params': pg}, rays, warp_extra={'alpha': alpha})
   torch.cuda.synchronize()
   for k in ('rgb', 'depth', 'acc'):

@@ -153,6 +153,12 @@ int nfb_warp_forward(nfb_handle* h, int num_points, const float* points,
 int nfb_set_profiling(nfb_handle* h, int enabled);
 float nfb_field_time_ms(nfb_handle* h, int level);
 
+/* Hardware self-test of the tcgen05 building blocks (UMMA descriptors, 128-byte
+ * swizzle, TMEM, bulk-copy ring): C[128,N] = bf16(A[128,K]) x bf16(W[K,N]), fp32
+ * accumulate.  K <= 320, N <= 256; device pointers. */
+int nfb_selftest_gemm(int K, int N, const float* A, const float* W, float* C,
+                      void* stream);
+
 /* Number of CUDA kernels this handle has launched so far (bench accounting). */
 long long nfb_kernel_launches(const nfb_handle* h);
 /* Thread-local description of the last error returned on this thread. */

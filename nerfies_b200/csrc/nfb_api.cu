@@ -13,6 +13,8 @@
 #include "common.cuh"
 #include "field_simt.cuh"
 #include "ray_kernels.cuh"
+#include "tc_common.cuh"
+#include "tc_selftest.cuh"
 #ifdef NFB_WITH_TC
 #include "field_tc.cuh"
 #endif
@@ -461,6 +463,31 @@ float nfb_field_time_ms(nfb_handle* h, int level) {
   float ms = -1.f;
   if (cudaEventElapsedTime(&ms, h->ev[level][0], h->ev[level][1]) != cudaSuccess) { fail("cudaEventElapsedTime failed"); return -1.f; }
   return ms;
+}
+
+int nfb_selftest_gemm(int K, int N, const float* A, const float* W, float* C, void* stream) {
+  using namespace nfb::tc;
+  if (K < 1 || K > kSelfMaxKb * kBlockK || N < 1 || N > 256) return fail("selftest: K<=320, N<=256");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int nkb = (K + kBlockK - 1) / kBlockK;
+  const int n_rows = (N + 15) / 16 * 16;
+  std::vector<int> k_map(nkb * kBlockK, -1);
+  for (int k = 0; k < K; ++k) k_map[k] = k;
+  int* d_map = nullptr;
+  __nv_bfloat16* d_w = nullptr;
+  NFB_CUDA(cudaMalloc(&d_map, k_map.size() * sizeof(int)));
+  NFB_CUDA(cudaMalloc(&d_w, (size_t)nkb * n_rows * kRowBytes));
+  NFB_CUDA(cudaMemcpyAsync(d_map, k_map.data(), k_map.size() * sizeof(int), cudaMemcpyHostToDevice, s));
+  const long long total = (long long)nkb * n_rows * kBlockK;
+  pack_weight_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(W, N, d_map, nkb, N, n_rows, d_w);
+  NFB_CUDA(cudaFuncSetAttribute(tc_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSelfSmemBytes));
+  tc_selftest_kernel<<<1, 160, kSelfSmemBytes, s>>>(A, K, d_w, nkb, n_rows, N, C);
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+  cudaFree(d_map);
+  cudaFree(d_w);
+  if (e != cudaSuccess) return fail("selftest kernel failed: %s", cudaGetErrorString(e));
+  return 0;
 }
 
 int nfb_create(const nfb_config* cfg, int max_rays, nfb_handle** out) {

@@ -1,0 +1,209 @@
+// tcgen05 / TMEM / mbarrier / bulk-copy primitives (inline PTX, sm_100a) and
+// the shared-memory operand format used by the tensor-core field kernel.
+//
+// Operand format ("K-major, 128-byte swizzle", the UMMA canonical layout
+// Swizzle<3,4,3> o ((8,m),(8,2)) of 16-byte units): an operand with R rows and
+// K columns of bf16 is cut into K-blocks of 64 columns.  One K-block is R rows
+// of 128 bytes; inside each row the eight 16-byte chunks are XOR-permuted with
+// (row & 7).  Blocks start on 1024-byte boundaries, 8-row groups are 1024 bytes
+// apart (the descriptor's stride byte offset).  One tcgen05.mma consumes K=16
+// (32 bytes of every row), so stepping K inside a block adds 32 bytes to the
+// descriptor's start address.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace nfb {
+namespace tc {
+
+constexpr int kBlockK = 64;              // bf16 columns per 128-byte swizzle row
+constexpr int kRowBytes = 128;
+constexpr int kTileRows = 128;           // rows of one A operand / accumulator
+constexpr int kABlockBytes = kTileRows * kRowBytes;   // 16 KB
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+
+// Byte offset of logical 16-byte chunk `chunk` (0..7) of row `row` in a K-block.
+__device__ __host__ __forceinline__ uint32_t swz_off(int row, int chunk) {
+  return (uint32_t)(row * kRowBytes + ((chunk ^ (row & 7)) << 4));
+}
+
+// ---- mbarrier ----------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_barrier_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+// Waits for the completion of the phase with the given parity.  A wait that
+// spins "forever" traps instead of hanging the GPU (a protocol bug, not a
+// condition that can occur in a correct run).
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t done = 0;
+  for (uint32_t spin = 0; !done; ++spin) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (!done && spin > (1u << 26)) {
+      printf("nfb: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", blockIdx.x,
+             threadIdx.x, addr, parity);
+      __trap();
+    }
+  }
+}
+
+// ---- bulk async copy (TMA engine, 1-D) -----------------------------------------
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes,
+                                         uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+          "r"(smem_u32(smem_dst)),
+      "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+// ---- TMEM ----------------------------------------------------------------------
+// Warp-collective.  Writes the allocated base address to *smem_slot.
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_slot, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                   smem_u32(smem_slot)),
+               "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols)
+               : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+// 32 consecutive accumulator columns of this thread's TMEM lane.
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+        "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]),
+        "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]),
+        "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+        "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() {
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// ---- UMMA descriptors ----------------------------------------------------------
+// Shared-memory matrix descriptor: K-major, SWIZZLE_128B, 8-row groups 1024 B
+// apart (cute::UMMA::SmemDescriptor: start>>4 [0,14), LBO>>4 [16,30),
+// SBO>>4 [32,46), version=1 [46,48), layout_type=2 [61,64)).
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+  uint64_t d = (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;           // leading byte offset (unused for swizzled K-major)
+  d |= (uint64_t)(1024 >> 4) << 32; // stride byte offset
+  d |= (uint64_t)1 << 46;           // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;           // SWIZZLE_128B
+  return d;
+}
+// Instruction descriptor for kind::f16, bf16 x bf16 -> f32, both K-major
+// (cute::UMMA::InstrDescriptor: c_format [4,6)=1, a_format [7,10)=1,
+// b_format [10,13)=1, n>>3 [17,23), m>>4 [24,29)).
+__device__ __host__ __forceinline__ uint32_t make_idesc_bf16(int m, int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) |
+         ((uint32_t)(m >> 4) << 24);
+}
+// D[tmem] (+)= A[smem] * B[smem]; issued by one thread.
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
+                                          uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// Arrives on `bar` when every tcgen05.mma issued so far by this thread is done.
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                   smem_u32(bar))
+               : "memory");
+}
+
+// ---- bf16 helpers ---------------------------------------------------------------
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+// Stores 8 consecutive K-columns (one 16-byte chunk) of `row` into a K-block.
+__device__ __forceinline__ void store_chunk(uint8_t* block, int row, int chunk, const float* v) {
+  uint4 q;
+  q.x = pack_bf16x2(v[0], v[1]);
+  q.y = pack_bf16x2(v[2], v[3]);
+  q.z = pack_bf16x2(v[4], v[5]);
+  q.w = pack_bf16x2(v[6], v[7]);
+  *reinterpret_cast<uint4*>(block + swz_off(row, chunk)) = q;
+}
+
+// Weight packing (global memory image of the shared-memory operand): the
+// (in,out) fp32 kernel W[k][n] of a Dense layer becomes, per K-block kb, a
+// contiguous unit of `n_rows` rows x 128 bytes holding W^T (row n, column k),
+// chunk-swizzled, zero-padded in K and N.  `k_map` lists for each of the nkb*64
+// packed K columns the source row of W (or -1 for padding), which is how the
+// skip concat [x, inputs] and the 64-column padding of the input block are laid
+// out.
+__global__ void pack_weight_kernel(const float* __restrict__ w_packed_fp32, int ld,
+                                   const int* __restrict__ k_map, int nkb, int n, int n_rows,
+                                   __nv_bfloat16* __restrict__ dst) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)nkb * n_rows * kBlockK;
+  if (idx >= total) return;
+  const int kk = (int)(idx % kBlockK);
+  const int row = (int)((idx / kBlockK) % n_rows);
+  const int kb = (int)(idx / ((long long)kBlockK * n_rows));
+  const int src_k = k_map[kb * kBlockK + kk];
+  float v = 0.f;
+  if (src_k >= 0 && row < n) v = w_packed_fp32[(size_t)src_k * ld + row];
+  uint8_t* unit = reinterpret_cast<uint8_t*>(dst) + (size_t)kb * n_rows * kRowBytes;
+  *reinterpret_cast<__nv_bfloat16*>(unit + swz_off(row, kk >> 3) + (kk & 7) * 2) =
+      __float2bfloat16_rn(v);
+}
+
+}  // namespace tc
+}  // namespace nfb

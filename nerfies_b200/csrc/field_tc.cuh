@@ -1,0 +1,574 @@
+// Fused per-sample field evaluation on the 5th-gen tensor cores
+// (NFB_PREC_BF16): bf16 operands, fp32 accumulation in TMEM.
+//
+// One persistent CTA per SM walks over "tile pairs" of 2 x 128 consecutive
+// (ray, sample) rows.  Every Dense layer of the warp MLP and the NeRF MLP is a
+// chain of tcgen05.mma (M=128 per sub-tile, K=16 each) whose
+//   A operand = the sub-tile's activations, bf16, in shared memory in the UMMA
+//               K-major 128B-swizzle format, written in place by the epilogue;
+//   B operand = pre-swizzled bf16 weight units streamed from L2 by
+//               cp.async.bulk through a 4-stage mbarrier ring, each unit used by
+//               both sub-tiles (256 rows per weight byte fetched);
+//   D         = fp32 accumulators in TMEM (2 sub-tiles x 256 columns).
+// Warp roles: warps 0-7 epilogue (one thread per row: tcgen05.ld -> bias ->
+// activation -> bf16 -> swizzled st.shared; also the SE(3) exp-map, the
+// positional encodings and the final sigmoid/softplus), warp 8 lane 0 issues the
+// MMAs, warp 9 lane 0 the weight copies.  The N dimension of a layer is issued
+// in two chunks so that the epilogue of chunk 0 overlaps the MMAs of chunk 1
+// and the next layer's first K-blocks overlap the epilogue of chunk 1.
+// Activations never leave the SM; per sample 16 B (r,g,b,sigma) go to HBM.
+#pragma once
+#include "field_simt.cuh"   // FieldArgs
+#include "nfb_handle.h"
+#include "tc_common.cuh"
+#include "tc_program.cuh"
+
+namespace nfb {
+namespace tc {
+
+constexpr int kStages = 4;
+constexpr int kStageBytes = 16384;              // 128 rows x 128 B
+constexpr int kTcThreads = 320;
+constexpr int kXBytes = 2 * 4 * kABlockBytes;   // 2 sub-tiles x 4 K-blocks
+constexpr int kInBytes = 2 * kABlockBytes;
+constexpr int kTcSmemBytes = 1024 + kXBytes + kInBytes + kStages * kStageBytes + 256;
+constexpr int kPairRows = 2 * kTileRows;
+
+struct TcBars {
+  uint64_t full[kStages];
+  uint64_t empty[kStages];
+  uint64_t acc_ready[2];
+  uint64_t x_free;
+  uint64_t x_ready[2];
+  uint32_t tmem_slot;
+};
+
+// Row state owned by one epilogue thread for the lifetime of a tile pair.
+struct RowState {
+  float x[3];        // current (possibly warped) sample point
+  long long m;       // global row (clamped to a valid row)
+  long long ray;
+  bool valid;
+  float alpha;       // running alpha-head dot product
+};
+
+// [x | w_k * sin/cos features | extra | 0...] -> one 64-column K-block row.
+__device__ __noinline__ void posenc_to_block(uint8_t* block, int r, const float* x, int F,
+                                             const float* __restrict__ window,
+                                             const float* __restrict__ extra, int n_extra) {
+  const int nf = 6 * F;
+#pragma unroll 1
+  for (int c = 0; c < 8; ++c) {
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int k = c * 8 + j;
+      float val = 0.f;
+      if (k < 3) {
+        val = x[k];
+      } else if (k < 3 + nf) {
+        const int f = k - 3;
+        val = posenc_feature(x, f);
+        if (window) val = __ldg(window + f / 6) * val;
+      } else if (k < 3 + nf + n_extra) {
+        val = __ldg(extra + (k - 3 - nf));
+      }
+      v[j] = val;
+    }
+    store_chunk(block, r, c, v);
+  }
+}
+
+__device__ __forceinline__ void cond_to_block(uint8_t* block, int r, const float* __restrict__ cond,
+                                              int n) {
+#pragma unroll 1
+  for (int c = 0; c < 8; ++c) {
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int k = c * 8 + j;
+      v[j] = k < n ? __ldg(cond + k) : 0.f;
+    }
+    store_chunk(block, r, c, v);
+  }
+}
+
+__global__ void __launch_bounds__(kTcThreads, 1)
+field_tc_kernel(const __grid_constant__ TcProgram prog, const FieldArgs args,
+                const uint8_t* __restrict__ wpack, const float* __restrict__ aux,
+                int num_pairs) {
+  extern __shared__ uint8_t raw[];
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* xbuf = base;                       // [2][4][16 KB]
+  uint8_t* inbuf = xbuf + kXBytes;            // [2][16 KB]
+  uint8_t* stages = inbuf + kInBytes;         // [kStages][16 KB]
+  TcBars* bars = reinterpret_cast<TcBars*>(stages + kStages * kStageBytes);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 256) {
+    for (int i = 0; i < kStages; ++i) { mbar_init(&bars->full[i], 1); mbar_init(&bars->empty[i], 1); }
+    mbar_init(&bars->acc_ready[0], 1); mbar_init(&bars->acc_ready[1], 1);
+    mbar_init(&bars->x_free, 1);
+    mbar_init(&bars->x_ready[0], 256); mbar_init(&bars->x_ready[1], 256);
+    fence_barrier_init();
+  }
+  if (warp == 8) tmem_alloc(&bars->tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = bars->tmem_slot;
+  const bool do_warp = args.use_warp && prog.warp_type != 0;
+  // Steps executed per tile pair: the warp net's steps come first in the list.
+  int first_step = 0;
+  if (!do_warp) {
+    while (first_step < prog.n_steps && prog.steps[first_step].epi != kEpiWarpHeads) ++first_step;
+    first_step = (first_step < prog.n_steps) ? first_step + 1 : 0;   // skip the warp net
+  }
+  int last_step = prog.n_steps - 1;
+  if (args.warp_only) {
+    last_step = 0;
+    while (prog.steps[last_step].epi != kEpiWarpHeads) ++last_step;
+  }
+
+  if (warp == 9) {
+    // ===================== weight producer =====================
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int pair = blockIdx.x; pair < num_pairs; pair += gridDim.x) {
+        for (int si = first_step; si <= last_step; ++si) {
+          const TcStep& st = prog.steps[si];
+          const uint32_t bytes = (uint32_t)st.chunk_n * kRowBytes;
+          const uint8_t* src = wpack + st.w_off;
+          for (int u = 0; u < st.n_chunks * st.nkb; ++u, ++it) {
+            const int sg = it % kStages;
+            const uint32_t ph = (it / kStages) & 1;
+            mbar_wait(&bars->empty[sg], ph ^ 1);
+            mbar_arrive_expect_tx(&bars->full[sg], bytes);
+            bulk_g2s(stages + sg * kStageBytes, src + (size_t)u * bytes, bytes, &bars->full[sg]);
+          }
+        }
+      }
+    }
+  } else if (warp == 8) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      uint32_t it = 0, xr = 0;
+      int prev_split = 99;   // first activation block produced by chunk 1 of the previous step
+      for (int pair = blockIdx.x; pair < num_pairs; pair += gridDim.x) {
+        for (int si = first_step; si <= last_step; ++si) {
+          const TcStep& st = prog.steps[si];
+          const uint32_t idesc = make_idesc_bf16(kTileRows, st.chunk_n);
+          mbar_wait(&bars->x_ready[0], xr & 1);
+          tc_fence_after();
+          bool have1 = false;
+          auto need1 = [&]() {
+            if (!have1) { mbar_wait(&bars->x_ready[1], xr & 1); tc_fence_after(); have1 = true; }
+          };
+          for (int c = 0; c < st.n_chunks; ++c) {
+            if (c == 1) need1();          // chunk-1 accumulator columns must be drained
+            for (int kb = 0; kb < st.nkb; ++kb, ++it) {
+              const int b = st.src[kb];
+              if (b < kSrcIn && b >= prev_split) need1();
+              const int sg = it % kStages;
+              mbar_wait(&bars->full[sg], (it / kStages) & 1);
+              tc_fence_after();
+              const uint32_t b_addr = smem_u32(stages + sg * kStageBytes);
+#pragma unroll
+              for (int s = 0; s < 2; ++s) {
+                const uint8_t* a_ptr = (b < kSrcIn) ? xbuf + (s * 4 + b) * kABlockBytes
+                                                    : inbuf + s * kABlockBytes;
+                const uint32_t a_addr = smem_u32(a_ptr);
+                const uint32_t d = tmem_base + s * 256 + c * st.chunk_n;
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                  umma_bf16(d, make_smem_desc(a_addr + k * 32), make_smem_desc(b_addr + k * 32),
+                            idesc, (kb | k) ? 1u : 0u);
+              }
+              umma_commit(&bars->empty[sg]);
+              if (c == 1 && kb == st.kb_free) umma_commit(&bars->x_free);
+            }
+            if (c == st.n_chunks - 1) need1();   // consume x_ready[1] before the epilogue can re-arm it
+            umma_commit(&bars->acc_ready[c]);
+            if (c == 0 && st.n_chunks == 2 && st.kb_free < 0) umma_commit(&bars->x_free);
+          }
+          ++xr;
+          prev_split = (st.n_chunks == 2) ? st.chunk_n / kBlockK : 99;
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue: one thread per row =====================
+    const int s = warp >> 2;                           // sub-tile
+    const int r = (warp & 3) * 32 + lane;              // row within the sub-tile
+    const uint32_t t_lane = tmem_base + (((uint32_t)(warp & 3) * 32) << 16) + s * 256;
+    uint8_t* xs = xbuf + s * 4 * kABlockBytes;
+    uint8_t* ins = inbuf + s * kABlockBytes;
+    uint32_t n_acc0 = 0, n_acc1 = 0, n_free = 0;
+    RowState row;
+    const int S = args.samples_per_ray;
+
+    auto arrive_both = [&]() {
+      fence_proxy_async();
+      tc_fence_before();
+      mbar_arrive(&bars->x_ready[0]);
+      mbar_arrive(&bars->x_ready[1]);
+    };
+    // Sample point of this thread's row for tile pair `pair`, and the first
+    // input block (model_utils.py:72-73; warping.py:325-326 / models.py:270).
+    auto begin_pair = [&](int pair) {
+      long long m = (long long)pair * kPairRows + s * kTileRows + r;
+      row.valid = m < args.num_rows;
+      if (!row.valid) m = args.num_rows - 1;
+      row.m = m;
+      row.ray = m / S;
+      const float z = args.z_vals ? __ldg(args.z_vals + m) : 0.f;
+#pragma unroll
+      for (int c = 0; c < 3; ++c)
+        row.x[c] = __ldg(args.origins + row.ray * 3 + c) + z * __ldg(args.directions + row.ray * 3 + c);
+      const float* cond = args.cond + row.ray * prog.cond_stride;
+      if (do_warp) {
+        posenc_to_block(ins, r, row.x, prog.Fw, args.window, cond, prog.G);
+      } else {
+        if (args.warped && row.valid) {
+#pragma unroll
+          for (int c = 0; c < 3; ++c) args.warped[m * 3 + c] = row.x[c];
+        }
+        posenc_to_block(ins, r, row.x, prog.Fp, nullptr, nullptr, 0);
+      }
+      row.alpha = __ldg(aux + prog.alpha_b_off);
+    };
+
+    int pair = blockIdx.x;
+    if (pair < num_pairs) {
+      begin_pair(pair);
+      arrive_both();
+    }
+    for (; pair < num_pairs; pair += gridDim.x) {
+      for (int si = first_step; si <= last_step; ++si) {
+        const TcStep& st = prog.steps[si];
+        const float* bias = aux + st.b_off;
+        if (st.epi == kEpiHidden) {
+          const int np = st.chunk_n / 32;              // 32-column pieces per chunk (2 or 4)
+          // ---- chunk 0: results are held in registers until the MMAs of chunk 1
+          //      no longer read the blocks they overwrite ----
+          uint32_t packed[64];
+          mbar_wait(&bars->acc_ready[0], n_acc0++ & 1);
+          tc_fence_after();
+#pragma unroll
+          for (int p = 0; p < 4; ++p) {
+            if (p < np) {
+              float v[32];
+              tmem_ld32(t_lane + p * 32, v);
+              tmem_ld_wait();
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                const float4 bq = __ldg(reinterpret_cast<const float4*>(bias + p * 32 + j));
+                v[j] += bq.x; v[j + 1] += bq.y; v[j + 2] += bq.z; v[j + 3] += bq.w;
+              }
+              if (st.relu) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+              }
+              if (st.alpha_dot) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                  const float4 wq = __ldg(reinterpret_cast<const float4*>(aux + prog.alpha_w_off + p * 32 + j));
+                  row.alpha = fmaf(v[j], wq.x, row.alpha); row.alpha = fmaf(v[j + 1], wq.y, row.alpha);
+                  row.alpha = fmaf(v[j + 2], wq.z, row.alpha); row.alpha = fmaf(v[j + 3], wq.w, row.alpha);
+                }
+              }
+#pragma unroll
+              for (int j = 0; j < 16; ++j) packed[p * 16 + j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+            }
+          }
+          mbar_wait(&bars->x_free, n_free++ & 1);
+#pragma unroll
+          for (int p = 0; p < 4; ++p) {
+            if (p < np) {
+              uint8_t* blk = xs + (p >> 1) * kABlockBytes;
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                uint4 o = make_uint4(packed[p * 16 + q * 4], packed[p * 16 + q * 4 + 1],
+                                     packed[p * 16 + q * 4 + 2], packed[p * 16 + q * 4 + 3]);
+                *reinterpret_cast<uint4*>(blk + swz_off(r, (p & 1) * 4 + q)) = o;
+              }
+            }
+          }
+          fence_proxy_async();
+          tc_fence_before();
+          mbar_arrive(&bars->x_ready[0]);
+          // ---- chunk 1: every MMA of the layer is complete, store directly ----
+          mbar_wait(&bars->acc_ready[1], n_acc1++ & 1);
+          tc_fence_after();
+#pragma unroll 1
+          for (int p = 0; p < np; ++p) {
+            float v[32];
+            const int col0 = st.chunk_n + p * 32;
+            tmem_ld32(t_lane + col0, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 bq = __ldg(reinterpret_cast<const float4*>(bias + col0 + j));
+              v[j] += bq.x; v[j + 1] += bq.y; v[j + 2] += bq.z; v[j + 3] += bq.w;
+            }
+            if (st.relu) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+            }
+            if (st.alpha_dot) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                const float4 wq = __ldg(reinterpret_cast<const float4*>(aux + prog.alpha_w_off + col0 + j));
+                row.alpha = fmaf(v[j], wq.x, row.alpha); row.alpha = fmaf(v[j + 1], wq.y, row.alpha);
+                row.alpha = fmaf(v[j + 2], wq.z, row.alpha); row.alpha = fmaf(v[j + 3], wq.w, row.alpha);
+              }
+            }
+            uint8_t* blk = xs + (col0 >> 6) * kABlockBytes;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) store_chunk(blk, r, ((col0 & 63) >> 3) + q, v + q * 8);
+          }
+          if (st.write_cond)
+            cond_to_block(ins, r, args.cond + row.ray * prog.cond_stride + prog.G, prog.rc);
+          fence_proxy_async();
+          tc_fence_before();
+          mbar_arrive(&bars->x_ready[1]);
+        } else {
+          // ---- heads: N = 16 accumulator columns, one chunk ----
+          float v[16];
+          mbar_wait(&bars->acc_ready[0], n_acc0++ & 1);
+          tc_fence_after();
+          tmem_ld16(t_lane, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] += __ldg(bias + j);
+          if (st.epi == kEpiWarpHeads) {
+            float y[3];
+            if (prog.warp_type == 2) {
+              se3_apply(v, row.x, y);
+            } else {
+#pragma unroll
+              for (int c = 0; c < 3; ++c) y[c] = row.x[c] + v[c];
+            }
+#pragma unroll
+            for (int c = 0; c < 3; ++c) row.x[c] = y[c];
+            if (args.warped && row.valid) {
+#pragma unroll
+              for (int c = 0; c < 3; ++c) args.warped[row.m * 3 + c] = y[c];
+            }
+            if (args.warp_only) {
+              // next pair's first input block, then hand over
+              const int nxt = pair + gridDim.x;
+              if (nxt < num_pairs) begin_pair(nxt);
+            } else {
+              posenc_to_block(ins, r, row.x, prog.Fp, nullptr, nullptr, 0);
+            }
+            arrive_both();
+          } else {
+            if (row.valid && args.samples) {
+              float4 o;
+              o.x = sigmoidf(v[0]); o.y = sigmoidf(v[1]); o.z = sigmoidf(v[2]);
+              o.w = apply_act(row.alpha, prog.sigma_act);
+              reinterpret_cast<float4*>(args.samples)[row.m] = o;
+            }
+            const int nxt = pair + gridDim.x;
+            if (nxt < num_pairs) begin_pair(nxt);
+            arrive_both();
+          }
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 8) tmem_dealloc(tmem_base, 512);
+}
+
+// ---------------------------------------------------------------------------
+// Host side: translate the model's layer list (FieldProgram, built for every
+// precision in nfb_api.cu) into TcPrograms, pack the weights, launch.
+// ---------------------------------------------------------------------------
+inline int tc_fail(const char* what) {
+  return fail("precision bf16 (tcgen05 path) does not support this model: %s; use precision fp32", what);
+}
+
+inline int build_tc_program(nfb_handle* h, int level, long long* wbytes, long long* aux_floats) {
+  const FieldProgram& fp = h->prog[level];
+  TcProgram& tp = h->tcprog[level];
+  memset(&tp, 0, sizeof(tp));
+  tp.warp_type = fp.warp_type; tp.Fw = fp.Fw; tp.G = fp.G; tp.Fp = fp.Fp; tp.rc = fp.rc;
+  tp.cond_stride = fp.cond_stride; tp.sigma_act = fp.sigma_act;
+  if (fp.tc || fp.ac) return tc_fail("trunk/alpha conditions");
+  if (fp.rc <= 0 || fp.rc > kBlockK) return tc_fail("rgb condition must have 1..64 channels");
+  if (fp.Dp > kBlockK || (fp.warp_type && fp.Dw > kBlockK)) return tc_fail("encoded inputs wider than 64");
+  if (fp.hidden_act != kRelu) return tc_fail("hidden activation other than relu");
+  auto new_bias = [&](const Step& st) {
+    int off = (int)*aux_floats;
+    *aux_floats += 256;
+    h->tc_aux_jobs.push_back({st.b_off, st.n, 1, off});
+    return off;
+  };
+  auto add = [&](const Step& st, int epi, int cur_width) -> int {
+    if (tp.n_steps >= kMaxTcSteps) return tc_fail("too many layers");
+    TcStep& t = tp.steps[tp.n_steps];
+    memset(&t, 0, sizeof(t));
+    if (st.k_x % kBlockK || st.k_x > 256 || st.k_in > kBlockK) return tc_fail("layer widths must be multiples of 64 (<= 256)");
+    if (st.k_x && st.k_x != cur_width) return tc_fail("unexpected layer input width");
+    t.nkb = 0;
+    for (int b = 0; b < st.k_x / kBlockK; ++b) t.src[t.nkb++] = b;
+    if (st.k_in) t.src[t.nkb++] = kSrcIn;
+    t.epi = epi;
+    if (epi == kEpiHidden) {
+      if (st.n != 128 && st.n != 256) return tc_fail("hidden widths must be 128 or 256");
+      t.n_chunks = 2; t.chunk_n = st.n / 2;
+      if (st.act != kRelu && st.act != kNone) return tc_fail("hidden activation other than relu");
+      t.relu = st.act == kRelu;
+      t.kb_free = -1;
+      for (int kb = 0; kb < t.nkb; ++kb)
+        if (t.src[kb] < kSrcIn && t.src[kb] < t.chunk_n / kBlockK) t.kb_free = kb;
+    } else {
+      t.n_chunks = 1; t.chunk_n = 16; t.kb_free = -1;
+      if (st.n > 8) return tc_fail("head wider than 8");
+    }
+    t.b_off = new_bias(st);
+    // weight units: for chunk c, for kb: chunk_n rows x 128 B
+    t.w_off = (uint32_t)*wbytes;
+    for (int c = 0; c < t.n_chunks; ++c) {
+      nfb_handle::TcPackJob job;
+      job.level = level; job.step = tp.n_steps; job.chunk = c;
+      job.simt_w_off = st.w_off; job.ld = st.npad; job.n = st.n; job.n0 = c * t.chunk_n;
+      job.k_map.assign((size_t)t.nkb * kBlockK, -1);
+      for (int kb = 0; kb < t.nkb; ++kb)
+        for (int j = 0; j < kBlockK; ++j) {
+          int srck = -1;
+          if (t.src[kb] < kSrcIn) srck = t.src[kb] * kBlockK + j;
+          else if (j < st.k_in) srck = st.k_x + j;
+          job.k_map[(size_t)kb * kBlockK + j] = srck;
+        }
+      h->tc_jobs.push_back(job);
+      *wbytes += (long long)t.nkb * t.chunk_n * kRowBytes;
+    }
+    tp.units_per_pair += t.n_chunks * t.nkb;
+    ++tp.n_steps;
+    return 0;
+  };
+  // warp net
+  int width = 0;
+  for (int i = 0; i < fp.warp.n_steps; ++i) {
+    const Step& st = fp.warp.steps[i];
+    const bool head = st.dst == kOut0 || st.dst == kOut1;
+    if (add(st, head ? kEpiWarpHeads : kEpiHidden, width)) return -1;
+    if (!head) width = st.n;
+  }
+  // nerf net: trunk..., [bottleneck], alpha head (folded), rgb branch
+  width = 0;
+  int last_hidden = -1;
+  bool seen_alpha = false, seen_bottleneck = false;
+  for (int i = 0; i < fp.nerf.n_steps; ++i) {
+    const Step& st = fp.nerf.steps[i];
+    if (st.dst == fp.alpha_slot && st.n == 1 && !seen_alpha) {
+      // alpha = Dense(1)(trunk_out): folded into the epilogue of the last trunk layer.
+      if (st.k_in) return tc_fail("alpha condition");
+      seen_alpha = true;
+      // The SIMT program runs bottleneck before alpha; the trunk's last layer is
+      // the hidden step before the bottleneck.
+      int trunk_last = seen_bottleneck ? last_hidden - 1 : last_hidden;
+      if (trunk_last < 0) return tc_fail("alpha head without a trunk layer");
+      tp.steps[trunk_last].alpha_dot = 1;
+      tp.alpha_w_off = (int)*aux_floats; *aux_floats += 256;
+      tp.alpha_b_off = (int)*aux_floats; *aux_floats += 4;
+      h->tc_aux_jobs.push_back({st.w_off, st.k_x, st.npad, tp.alpha_w_off});
+      h->tc_aux_jobs.push_back({st.b_off, 1, 1, tp.alpha_b_off});
+      continue;
+    }
+    const bool out = st.dst == fp.rgb_slot;
+    if (!out && st.act == kNone) {                 // bottleneck
+      seen_bottleneck = true;
+    }
+    if (add(st, out ? kEpiRgbOut : kEpiHidden, width)) return -1;
+    if (!out) {
+      last_hidden = tp.n_steps - 1;
+      width = st.n;
+      if (st.act == kNone) tp.steps[last_hidden].write_cond = 1;
+    }
+  }
+  if (!seen_alpha || !seen_bottleneck) return tc_fail("model without bottleneck/alpha head");
+  return 0;
+}
+
+inline int create_tc(nfb_handle* h) {
+  long long wbytes = 0, auxf = 0;
+  h->tc_jobs.clear(); h->tc_aux_jobs.clear();
+  const int levels = h->cfg.num_fine_samples > 0 ? 2 : 1;
+  for (int lv = 0; lv < levels; ++lv)
+    if (build_tc_program(h, lv, &wbytes, &auxf)) return -1;
+  if (levels == 1) h->tcprog[1] = h->tcprog[0];
+  h->wpack_bytes = wbytes; h->aux_floats = auxf;
+  if (cudaMalloc(&h->d_wpack, (size_t)wbytes) != cudaSuccess) return fail("cudaMalloc wpack failed");
+  if (cudaMalloc(&h->d_aux, (size_t)auxf * sizeof(float)) != cudaSuccess) return fail("cudaMalloc aux failed");
+  if (cudaMemset(h->d_aux, 0, (size_t)auxf * sizeof(float)) != cudaSuccess) return fail("cudaMemset failed");
+  if (cudaFuncSetAttribute(field_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes) != cudaSuccess)
+    return fail("cannot reserve %d bytes of shared memory for the tcgen05 kernel", kTcSmemBytes);
+  return 0;
+}
+
+inline void destroy_tc(nfb_handle* h) {
+  if (h->d_wpack) cudaFree(h->d_wpack);
+  if (h->d_aux) cudaFree(h->d_aux);
+  h->d_wpack = nullptr; h->d_aux = nullptr;
+}
+
+__global__ void aux_copy_kernel(const float* __restrict__ src, int count, int stride,
+                                float* __restrict__ dst) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < count) dst[i] = src[(size_t)i * stride];
+}
+
+// Called from nfb_set_params after the fp32 layout has been filled.
+inline int pack_tc(nfb_handle* h, cudaStream_t s) {
+  // k_maps are small; one staging buffer, stream-ordered.
+  size_t total_map = 0;
+  for (auto& j : h->tc_jobs) total_map += j.k_map.size();
+  int* d_maps = nullptr;
+  if (cudaMalloc(&d_maps, total_map * sizeof(int)) != cudaSuccess) return fail("cudaMalloc k_map failed");
+  std::vector<int> all;
+  all.reserve(total_map);
+  for (auto& j : h->tc_jobs) all.insert(all.end(), j.k_map.begin(), j.k_map.end());
+  cudaError_t e = cudaMemcpyAsync(d_maps, all.data(), total_map * sizeof(int), cudaMemcpyHostToDevice, s);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s);   // `all` is pageable and local
+  if (e != cudaSuccess) { cudaFree(d_maps); return fail("k_map upload failed: %s", cudaGetErrorString(e)); }
+  size_t map_off = 0;
+  for (auto& j : h->tc_jobs) {
+    const TcStep& t = h->tcprog[j.level].steps[j.step];
+    const long long total = (long long)t.nkb * t.chunk_n * kBlockK;
+    uint8_t* dst = h->d_wpack + t.w_off + (size_t)j.chunk * t.nkb * t.chunk_n * kRowBytes;
+    // source columns n0.. of the fp32 (K x npad) matrix: shift the base pointer.
+    pack_weight_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(
+        h->d_packed + j.simt_w_off + j.n0, j.ld, d_maps + map_off, t.nkb, j.n - j.n0, t.chunk_n,
+        reinterpret_cast<__nv_bfloat16*>(dst));
+    h->launches++;
+    map_off += j.k_map.size();
+  }
+  for (auto& a : h->tc_aux_jobs) {
+    aux_copy_kernel<<<(a.count + 127) / 128, 128, 0, s>>>(h->d_packed + a.src_off, a.count, a.stride,
+                                                          h->d_aux + a.dst_off);
+    h->launches++;
+  }
+  e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+  cudaFree(d_maps);
+  if (e != cudaSuccess) return fail("tcgen05 weight packing failed: %s", cudaGetErrorString(e));
+  return 0;
+}
+
+inline int run_field_tc(nfb_handle* h, int level, const FieldArgs& a, cudaStream_t s) {
+  const long long pairs = (a.num_rows + kPairRows - 1) / kPairRows;
+  const int grid = (int)std::min<long long>(pairs, h->sm_count);
+  field_tc_kernel<<<grid, kTcThreads, kTcSmemBytes, s>>>(h->tcprog[level], a, h->d_wpack, h->d_aux, (int)pairs);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail("field_tc_kernel launch failed: %s", cudaGetErrorString(e));
+  h->launches++;
+  return 0;
+}
+
+}  // namespace tc
+}  // namespace nfb

@@ -11,6 +11,7 @@
 
 #include "../../include/nerfies_b200.h"
 #include "common.cuh"
+#include "nfb_handle.h"
 #include "field_simt.cuh"
 #include "ray_kernels.cuh"
 #include "tc_common.cuh"
@@ -18,80 +19,6 @@
 #ifdef NFB_WITH_TC
 #include "field_tc.cuh"
 #endif
-
-namespace {
-
-thread_local std::string g_error;
-
-int fail(const char* fmt, ...) {
-  char buf[1024];
-  va_list ap;
-  va_start(ap, fmt);
-  vsnprintf(buf, sizeof(buf), fmt, ap);
-  va_end(ap);
-  g_error = buf;
-  return -1;
-}
-
-#define NFB_CUDA(expr)                                                        \
-  do {                                                                        \
-    cudaError_t e_ = (expr);                                                  \
-    if (e_ != cudaSuccess)                                                    \
-      return fail("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_),     \
-                  __FILE__, __LINE__);                                        \
-  } while (0)
-
-struct ParamSpec {
-  std::string name;
-  long long rows, cols;
-  // destination in the packed buffer: element (r, c) -> dst_off + r * ld + c_off + c
-  long long dst_off;
-  int ld, c_off;
-  int table;  // 0 = packed dense buffer; 1/2/3 = warp/appearance/camera table
-};
-
-__global__ void pack_kernel(const float* __restrict__ src, float* __restrict__ dst,
-                            long long rows, long long cols, int ld, int c_off) {
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= rows * cols) return;
-  const long long r = idx / cols, c = idx - r * cols;
-  dst[r * ld + c_off + c] = src[idx];
-}
-
-int pad32(int n) { return (n + 31) / 32 * 32; }
-
-}  // namespace
-
-struct nfb_handle {
-  nfb_config cfg;
-  int max_rays = 0;
-  int device = 0;
-  nfb::FieldProgram prog[2];          // per level (coarse, fine)
-  std::vector<ParamSpec> specs;
-  long long packed_floats = 0;
-  float* d_packed = nullptr;          // dense weights/biases (both levels + warp)
-  float* d_warp_table = nullptr;
-  float* d_app_table = nullptr;
-  float* d_cam_table = nullptr;
-  bool params_set = false;
-  // per-model tables
-  float *d_zlin = nullptr, *d_lower = nullptr, *d_upper = nullptr, *d_ulin = nullptr;
-  float* d_window = nullptr;
-  float h_window_alpha = NAN;
-  // workspace
-  float *d_cond = nullptr, *d_zc = nullptr, *d_zf = nullptr, *d_wc = nullptr;
-  float* d_samples = nullptr;
-  float *d_out_c = nullptr, *d_out_f = nullptr;
-  // device + pinned staging for the *_host entry point
-  float *d_in = nullptr, *h_in = nullptr, *h_out = nullptr;
-  unsigned *d_ids = nullptr, *h_ids = nullptr;
-  long long launches = 0;
-  bool profiling = false;
-  cudaEvent_t ev[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
-  bool ev_valid[2] = {false, false};
-  int cond_stride = 0;
-  int sm_count = 148;
-};
 
 namespace {
 

@@ -1,0 +1,37 @@
+// Step list interpreted by the tensor-core field kernel (field_tc.cuh).
+#pragma once
+#include <stdint.h>
+
+namespace nfb {
+namespace tc {
+
+constexpr int kMaxTcSteps = 24;
+constexpr int kSrcIn = 4;     // K-block source: 0..3 = activation block, 4 = input block
+
+enum Epi { kEpiHidden = 0, kEpiWarpHeads = 1, kEpiRgbOut = 2 };
+
+// One Dense layer as a chain of tcgen05.mma over K-blocks of 64 columns.
+struct TcStep {
+  uint32_t w_off;      // byte offset of the first weight unit (bf16, pre-swizzled)
+  int nkb;             // K-blocks
+  int src[6];          // per K-block source
+  int n_chunks;        // the N dimension is issued as 1 or 2 chunks ...
+  int chunk_n;         // ... of this many columns (multiple of 16)
+  int b_off;           // float offset of the bias (256 floats reserved) in the aux buffer
+  int epi;             // Epi
+  int relu;            // hidden activation (relu) or identity (bottleneck)
+  int alpha_dot;       // this epilogue also accumulates the alpha head (Dense(1))
+  int write_cond;      // this epilogue also writes the rgb condition into the input block
+  int kb_free;         // chunk 1 commits "chunk-0 destination blocks are free" after this kb
+};
+
+struct TcProgram {
+  int n_steps;
+  TcStep steps[kMaxTcSteps];
+  int warp_type, Fw, G, Fp, rc, cond_stride, sigma_act;
+  int alpha_w_off, alpha_b_off;   // aux float offsets
+  uint32_t units_per_pair;        // weight units streamed per tile pair
+};
+
+}  // namespace tc
+}  // namespace nfb

@@ -177,8 +177,31 @@ def sinusoidal_encode(x: Tensor, num_freqs: int,
 # --------------------------------------------------------------------------
 # MLP  (modules.py:26-62)
 # --------------------------------------------------------------------------
-def dense(p: Dict[str, Tensor], x: Tensor) -> Tensor:
-  return x @ p['kernel'].to(x.dtype) + p['bias'].to(x.dtype)
+# When set, dense() rounds both operands to bfloat16 and accumulates in fp32:
+# the arithmetic of the tensor-core path (NFB_PREC_BF16), so that its wiring can
+# be checked at a tolerance far below bf16's own 4e-3 rounding.
+_BF16_OPERANDS = False
+
+
+class bf16_operands:
+  """Context manager: emulate bf16-operand / fp32-accumulate Dense layers."""
+
+  def __enter__(self):
+    global _BF16_OPERANDS
+    self._old = _BF16_OPERANDS
+    _BF16_OPERANDS = True
+
+  def __exit__(self, *exc):
+    global _BF16_OPERANDS
+    _BF16_OPERANDS = self._old
+
+
+def dense(p: Dict[str, Tensor], x: Tensor, exact: bool = False) -> Tensor:
+  k = p['kernel'].to(x.dtype)
+  if _BF16_OPERANDS and not exact:
+    x = x.bfloat16().to(x.dtype)
+    k = k.bfloat16().to(k.dtype)
+  return x @ k + p['bias'].to(x.dtype)
 
 
 def mlp(params: Dict[str, Any], x: Tensor, depth: int, skips: Sequence[int],
@@ -312,8 +335,12 @@ def nerf_mlp(params: Dict[str, Any], spec: OracleSpec, x: Tensor,
     alpha_input = torch.cat([bottleneck, bc(alpha_condition)], dim=-1)
   else:
     alpha_input = h
-  alpha = mlp(params['MLP_2'], alpha_input, 0, (), spec.activation,
-              has_logit=True)
+  if alpha_condition is None:
+    # (the tensor-core path evaluates this Dense(1) in fp32 on CUDA cores)
+    alpha = dense(params['MLP_2']['logit'], alpha_input, exact=True)
+  else:
+    alpha = mlp(params['MLP_2'], alpha_input, 0, (), spec.activation,
+                has_logit=True)
   if rgb_condition is not None:
     rgb_input = torch.cat([bottleneck, bc(rgb_condition)], dim=-1)
   else:

@@ -332,3 +332,102 @@ def test_errors_are_loud():
   bad = {k: v for k, v in bad.items() if k != 'warp_field'}
   with pytest.raises(KeyError):
     hd.set_params(tree_to_device(bad, DEV))
+
+
+# ---------------------------------------------------------------------------
+# Tensor-core path (precision='bf16'): bf16 operands, fp32 accumulation.
+# Checked two ways: tightly against the oracle run with the same operand
+# rounding (wiring / layout / pipeline bugs), and loosely against the fp32
+# reference (what bf16 costs; reported).
+# ---------------------------------------------------------------------------
+TOL_BF16_WIRING = 3e-3
+
+
+def _bf16_case(dims):
+  if dims == 'quarterhd':
+    spec = O.OracleSpec(num_coarse_samples=128, num_fine_samples=128,
+                        near=0.02, far=0.83, num_nerf_point_freqs=8,
+                        sigma_activation='softplus', use_warp=True,
+                        use_appearance_metadata=True, num_warp_embeddings=200,
+                        num_appearance_embeddings=200)
+    return spec, 70, 8.0       # 70*128 rows: ragged last tile pair
+  if dims == 'vrig':
+    spec = O.OracleSpec(num_coarse_samples=128, num_fine_samples=128,
+                        near=0.02, far=0.83, num_nerf_point_freqs=8,
+                        num_warp_freqs=6, sigma_activation='softplus',
+                        use_warp=True, use_camera_metadata=True,
+                        num_warp_embeddings=150, num_camera_embeddings=2)
+    return spec, 64, 2.7
+  if dims == 'test_local':
+    spec = O.OracleSpec(num_coarse_samples=64, num_fine_samples=64, near=0.02,
+                        far=0.83, num_nerf_point_freqs=10, num_warp_features=3,
+                        sigma_activation='softplus', use_warp=True,
+                        use_appearance_metadata=True, num_warp_embeddings=20,
+                        num_appearance_embeddings=20)
+    return spec, 37, 5.5
+  spec = O.OracleSpec(num_coarse_samples=96, num_fine_samples=32, near=0.1,
+                      far=1.5, num_nerf_point_freqs=10, sigma_activation='relu',
+                      use_warp=False, use_white_background=True)
+  return spec, 50, 0.0
+
+
+@pytest.mark.parametrize('dims', ['quarterhd', 'vrig', 'test_local', 'nowarp'])
+def test_bf16_levels_vs_bf16_oracle(dims):
+  spec, n, alpha = _bf16_case(dims)
+  p = O.make_trained_like(O.init_params(spec, 21), seed=22)
+  rays = O.synthetic_rays(n, spec, seed=23)
+  model = model_from_spec(spec_to_dict(spec), precision='bf16', device=DEV,
+                          batch_size=n)
+  pg = tree_to_device(p, DEV)
+  ref32 = O.render_forward(p, spec, rays, warp_alpha=alpha)
+  for lv, level in ((0, 'coarse'), (1, 'fine')):
+    z = ref32[level]['z_vals']
+    got = _render_level(model, pg, lv, rays, z, alpha)
+    with O.bf16_operands():
+      ref = O.render_level(p, spec, level, rays, z, alpha)
+    keys = ['rgb', 'depth', 'acc', 'weights']
+    if spec.use_warp:
+      keys.append('warped_points')
+    for k in keys:
+      err = rel_err(got[k], ref[k])
+      e32 = rel_err(got[k], ref32[level][k])
+      _REPORT.append((f'bf16:{dims}', level, k, err, e32))
+      assert err < TOL_BF16_WIRING, f'{dims} {level}/{k}: {err:.3e}'
+    err_s = rel_err(got['samples'], torch.cat(
+        [ref['sample_rgb'], ref['sample_sigma'][..., None]], -1))
+    assert err_s < 2e-2, f'{dims} {level}/samples: {err_s:.3e}'
+
+
+def test_bf16_end_to_end_and_host_path():
+  spec, n, alpha = _bf16_case('quarterhd')
+  p = O.make_trained_like(O.init_params(spec, 31), seed=32)
+  rays = O.synthetic_rays(300, spec, seed=33)
+  model = model_from_spec(spec_to_dict(spec), precision='bf16', device=DEV,
+                          batch_size=300)
+  pg = tree_to_device(p, DEV)
+  out = model.apply({'params': pg}, rays, warp_extra={'alpha': alpha},
+                    return_weights=True)
+  out2 = model.apply({'params': pg}, rays, warp_extra={'alpha': alpha},
+                     return_weights=True)
+  torch.cuda.synchronize()
+  for lv in ('coarse', 'fine'):
+    for k in ('rgb', 'depth', 'med_depth', 'acc', 'weights'):
+      assert torch.equal(out[lv][k], out2[lv][k]), (lv, k)   # deterministic
+  ref = O.render_forward(p, spec, rays, warp_alpha=alpha)
+  mse = float(((out['fine']['rgb'].cpu() - ref['fine']['rgb'])**2).mean())
+  psnr = -10 * np.log10(max(mse, 1e-20))
+  _REPORT.append(('bf16:e2e', 'fine', 'psnr_db_vs_fp32_oracle', psnr, 0.0))
+  assert psnr > 35, f'bf16 end-to-end PSNR vs fp32 oracle {psnr:.1f} dB'
+  sub = slice(100, 171)
+  rs = {'origins': rays['origins'][sub], 'directions': rays['directions'][sub],
+        'metadata': {k: v[sub] for k, v in rays['metadata'].items()}}
+  out3 = model.apply({'params': pg}, rs, warp_extra={'alpha': alpha})
+  assert torch.equal(out3['fine']['rgb'], out['fine']['rgb'][sub])
+
+
+def test_bf16_rejects_unsupported_models():
+  from nerfies_b200 import _lib
+  g = Golden('se3_small')   # 64-wide trunk: not a tensor-core shape
+  model = model_from_spec(g.spec_dict, precision='bf16', device=DEV)
+  with pytest.raises(_lib.NfbError, match='precision fp32'):
+    model.handle(16)

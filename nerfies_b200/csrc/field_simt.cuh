@@ -45,6 +45,7 @@ struct FieldArgs {
   int samples_per_ray;       // S
   int use_warp;              // run the warp net
   int warp_only;             // stop after the warp (nfb_warp_forward)
+  int fast_encode;           // bf16 mode: octave-recurrence positional encoding
 };
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {

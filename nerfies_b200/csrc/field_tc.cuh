@@ -31,7 +31,10 @@ constexpr int kStageBytes = 16384;              // 128 rows x 128 B
 constexpr int kTcThreads = 320;
 constexpr int kXBytes = 2 * 4 * kABlockBytes;   // 2 sub-tiles x 4 K-blocks
 constexpr int kInBytes = 2 * kABlockBytes;
-constexpr int kTcSmemBytes = 1024 + kXBytes + kInBytes + kStages * kStageBytes + 256;
+constexpr int kBiasBytes = 2 * 256 * 4;          // double-buffered per-step biases
+// No alignment slack: the dynamic shared-memory window of a kernel without static
+// shared memory starts 1024-byte aligned (checked at run time, trap otherwise).
+constexpr int kTcSmemBytes = kXBytes + kInBytes + kStages * kStageBytes + kBiasBytes + 128;
 constexpr int kPairRows = 2 * kTileRows;
 
 struct TcBars {
@@ -42,6 +45,7 @@ struct TcBars {
   uint64_t x_ready[2];
   uint32_t tmem_slot;
 };
+static_assert(sizeof(TcBars) <= 128, "barrier block");
 
 // Row state owned by one epilogue thread for the lifetime of a tile pair.
 struct RowState {
@@ -79,6 +83,78 @@ __device__ __noinline__ void posenc_to_block(uint8_t* block, int r, const float*
   }
 }
 
+// bf16 mode: the encoded features are rounded to bf16 (rel. 4e-3) before they
+// reach the tensor cores, so the octave recurrence
+//   sin 2a = 2 sin a cos a,  cos 2a = 1 - 2 sin^2 a
+// (error doubles per octave: < 1e-4 at 2^9) replaces 6F libm calls by 3 sincosf.
+__device__ __noinline__ void posenc_fast_to_block(uint8_t* block, int r, const float* x, int F,
+                                                  const float* __restrict__ window,
+                                                  const float* __restrict__ extra, int n_extra) {
+  float feat[64];
+#pragma unroll
+  for (int k = 0; k < 64; ++k) feat[k] = 0.f;
+  float sn[3], cs[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    feat[c] = x[c];
+    sincosf(x[c], &sn[c], &cs[c]);
+  }
+#pragma unroll
+  for (int f = 0; f < 10; ++f) {
+    if (f < F) {
+      const float w = window ? __ldg(window + f) : 1.f;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        feat[3 + f * 6 + c] = w * sn[c];
+        feat[3 + f * 6 + 3 + c] = w * cs[c];
+        const float s2 = 2.f * sn[c] * cs[c];
+        const float c2 = 1.f - 2.f * sn[c] * sn[c];
+        sn[c] = s2; cs[c] = c2;
+      }
+    }
+  }
+  const int d = 3 + 6 * F;
+#pragma unroll
+  for (int k = 0; k < 64; ++k) {
+    // `extra` (GLO code) sits right after the encoding; k is compile-time, d is not.
+    if (k >= d && k < d + n_extra) feat[k] = __ldg(extra + (k - d));
+  }
+#pragma unroll
+  for (int c = 0; c < 8; ++c) store_chunk(block, r, c, feat + c * 8);
+}
+
+// One 32-column piece of a hidden layer's epilogue: + bias, (alpha head dot),
+// round to bf16, ReLU on the packed pairs (rounding is monotone and keeps zero,
+// so relu-then-round == round-then-relu).
+__device__ __forceinline__ void epi_piece(const float* v, const float* __restrict__ bias32,
+                                          bool relu, bool adot,
+                                          const float* __restrict__ alpha_w32, float& alpha,
+                                          uint32_t* out16) {
+  float t[32];
+#pragma unroll
+  for (int j = 0; j < 32; j += 4) {
+    const float4 bq = *reinterpret_cast<const float4*>(bias32 + j);
+    t[j] = v[j] + bq.x; t[j + 1] = v[j + 1] + bq.y; t[j + 2] = v[j + 2] + bq.z; t[j + 3] = v[j + 3] + bq.w;
+  }
+  if (adot) {
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      const float4 wq = __ldg(reinterpret_cast<const float4*>(alpha_w32 + j));
+      alpha = fmaf(fmaxf(t[j], 0.f), wq.x, alpha);
+      alpha = fmaf(fmaxf(t[j + 1], 0.f), wq.y, alpha);
+      alpha = fmaf(fmaxf(t[j + 2], 0.f), wq.z, alpha);
+      alpha = fmaf(fmaxf(t[j + 3], 0.f), wq.w, alpha);
+    }
+  }
+  const __nv_bfloat162 zero = __float2bfloat162_rn(0.f);
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    __nv_bfloat162 pk = __floats2bfloat162_rn(t[2 * j], t[2 * j + 1]);
+    if (relu) pk = __hmax2(pk, zero);
+    out16[j] = *reinterpret_cast<uint32_t*>(&pk);
+  }
+}
+
 __device__ __forceinline__ void cond_to_block(uint8_t* block, int r, const float* __restrict__ cond,
                                               int n) {
 #pragma unroll 1
@@ -97,12 +173,17 @@ __global__ void __launch_bounds__(kTcThreads, 1)
 field_tc_kernel(const __grid_constant__ TcProgram prog, const FieldArgs args,
                 const uint8_t* __restrict__ wpack, const float* __restrict__ aux,
                 int num_pairs) {
-  extern __shared__ uint8_t raw[];
-  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~uintptr_t(1023));
+  extern __shared__ __align__(1024) uint8_t raw[];
+  uint8_t* base = raw;
+  if ((smem_u32(base) & 1023u) != 0) {
+    if (threadIdx.x == 0) printf("nfb: dynamic shared memory is not 1024-byte aligned\n");
+    __trap();
+  }
   uint8_t* xbuf = base;                       // [2][4][16 KB]
   uint8_t* inbuf = xbuf + kXBytes;            // [2][16 KB]
   uint8_t* stages = inbuf + kInBytes;         // [kStages][16 KB]
-  TcBars* bars = reinterpret_cast<TcBars*>(stages + kStages * kStageBytes);
+  float* bias_s = reinterpret_cast<float*>(stages + kStages * kStageBytes);   // [2][256]
+  TcBars* bars = reinterpret_cast<TcBars*>(reinterpret_cast<uint8_t*>(bias_s) + kBiasBytes);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 256) {
@@ -203,7 +284,8 @@ field_tc_kernel(const __grid_constant__ TcProgram prog, const FieldArgs args,
     const uint32_t t_lane = tmem_base + (((uint32_t)(warp & 3) * 32) << 16) + s * 256;
     uint8_t* xs = xbuf + s * 4 * kABlockBytes;
     uint8_t* ins = inbuf + s * kABlockBytes;
-    uint32_t n_acc0 = 0, n_acc1 = 0, n_free = 0;
+    uint32_t n_acc0 = 0, n_acc1 = 0, n_free = 0, n_step = 0;
+    float next_bias = __ldg(aux + prog.steps[first_step].b_off + tid);
     RowState row;
     const int S = args.samples_per_ray;
 
@@ -227,13 +309,15 @@ field_tc_kernel(const __grid_constant__ TcProgram prog, const FieldArgs args,
         row.x[c] = __ldg(args.origins + row.ray * 3 + c) + z * __ldg(args.directions + row.ray * 3 + c);
       const float* cond = args.cond + row.ray * prog.cond_stride;
       if (do_warp) {
-        posenc_to_block(ins, r, row.x, prog.Fw, args.window, cond, prog.G);
+        if (args.fast_encode) posenc_fast_to_block(ins, r, row.x, prog.Fw, args.window, cond, prog.G);
+        else posenc_to_block(ins, r, row.x, prog.Fw, args.window, cond, prog.G);
       } else {
         if (args.warped && row.valid) {
 #pragma unroll
           for (int c = 0; c < 3; ++c) args.warped[m * 3 + c] = row.x[c];
         }
-        posenc_to_block(ins, r, row.x, prog.Fp, nullptr, nullptr, 0);
+        if (args.fast_encode) posenc_fast_to_block(ins, r, row.x, prog.Fp, nullptr, nullptr, 0);
+        else posenc_to_block(ins, r, row.x, prog.Fp, nullptr, nullptr, 0);
       }
       row.alpha = __ldg(aux + prog.alpha_b_off);
     };
@@ -246,39 +330,35 @@ field_tc_kernel(const __grid_constant__ TcProgram prog, const FieldArgs args,
     for (; pair < num_pairs; pair += gridDim.x) {
       for (int si = first_step; si <= last_step; ++si) {
         const TcStep& st = prog.steps[si];
-        const float* bias = aux + st.b_off;
+        // This step's biases: staged in shared memory by the 256 epilogue threads
+        // (value prefetched during the previous step), next step's prefetched now.
+        float* bias = bias_s + (n_step & 1) * 256;
+        bias[tid] = next_bias;
+        {
+          int nsi = si + 1, npair = pair;
+          if (nsi > last_step) { nsi = first_step; npair = pair + gridDim.x; }
+          if (npair < num_pairs) next_bias = __ldg(aux + prog.steps[nsi].b_off + tid);
+        }
+        ++n_step;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
         if (st.epi == kEpiHidden) {
           const int np = st.chunk_n / 32;              // 32-column pieces per chunk (2 or 4)
+          const bool relu = st.relu != 0, adot = st.alpha_dot != 0;
+          const float* aw = aux + prog.alpha_w_off;
           // ---- chunk 0: results are held in registers until the MMAs of chunk 1
           //      no longer read the blocks they overwrite ----
           uint32_t packed[64];
           mbar_wait(&bars->acc_ready[0], n_acc0++ & 1);
           tc_fence_after();
 #pragma unroll
-          for (int p = 0; p < 4; ++p) {
-            if (p < np) {
-              float v[32];
-              tmem_ld32(t_lane + p * 32, v);
+          for (int pp = 0; pp < 2; ++pp) {
+            if (2 * pp < np) {
+              float va[32], vb[32];
+              tmem_ld32(t_lane + (2 * pp) * 32, va);
+              tmem_ld32(t_lane + (2 * pp + 1) * 32, vb);
               tmem_ld_wait();
-#pragma unroll
-              for (int j = 0; j < 32; j += 4) {
-                const float4 bq = __ldg(reinterpret_cast<const float4*>(bias + p * 32 + j));
-                v[j] += bq.x; v[j + 1] += bq.y; v[j + 2] += bq.z; v[j + 3] += bq.w;
-              }
-              if (st.relu) {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
-              }
-              if (st.alpha_dot) {
-#pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                  const float4 wq = __ldg(reinterpret_cast<const float4*>(aux + prog.alpha_w_off + p * 32 + j));
-                  row.alpha = fmaf(v[j], wq.x, row.alpha); row.alpha = fmaf(v[j + 1], wq.y, row.alpha);
-                  row.alpha = fmaf(v[j + 2], wq.z, row.alpha); row.alpha = fmaf(v[j + 3], wq.w, row.alpha);
-                }
-              }
-#pragma unroll
-              for (int j = 0; j < 16; ++j) packed[p * 16 + j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+              epi_piece(va, bias + (2 * pp) * 32, relu, adot, aw + (2 * pp) * 32, row.alpha, packed + (2 * pp) * 16);
+              epi_piece(vb, bias + (2 * pp + 1) * 32, relu, adot, aw + (2 * pp + 1) * 32, row.alpha, packed + (2 * pp + 1) * 16);
             }
           }
           mbar_wait(&bars->x_free, n_free++ & 1);
@@ -300,32 +380,25 @@ field_tc_kernel(const __grid_constant__ TcProgram prog, const FieldArgs args,
           // ---- chunk 1: every MMA of the layer is complete, store directly ----
           mbar_wait(&bars->acc_ready[1], n_acc1++ & 1);
           tc_fence_after();
-#pragma unroll 1
-          for (int p = 0; p < np; ++p) {
-            float v[32];
-            const int col0 = st.chunk_n + p * 32;
-            tmem_ld32(t_lane + col0, v);
-            tmem_ld_wait();
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const float4 bq = __ldg(reinterpret_cast<const float4*>(bias + col0 + j));
-              v[j] += bq.x; v[j + 1] += bq.y; v[j + 2] += bq.z; v[j + 3] += bq.w;
-            }
-            if (st.relu) {
+          for (int pp = 0; pp < 2; ++pp) {
+            if (2 * pp < np) {
+              float va[32], vb[32];
+              const int col0 = st.chunk_n + 2 * pp * 32;
+              tmem_ld32(t_lane + col0, va);
+              tmem_ld32(t_lane + col0 + 32, vb);
+              tmem_ld_wait();
+              uint32_t pk[32];
+              epi_piece(va, bias + col0, relu, adot, aw + col0, row.alpha, pk);
+              epi_piece(vb, bias + col0 + 32, relu, adot, aw + col0 + 32, row.alpha, pk + 16);
+              // 64 columns = one K-block row (col0 is a multiple of 64)
+              uint8_t* blk = xs + (col0 >> 6) * kABlockBytes;
 #pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
-            }
-            if (st.alpha_dot) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 4) {
-                const float4 wq = __ldg(reinterpret_cast<const float4*>(aux + prog.alpha_w_off + col0 + j));
-                row.alpha = fmaf(v[j], wq.x, row.alpha); row.alpha = fmaf(v[j + 1], wq.y, row.alpha);
-                row.alpha = fmaf(v[j + 2], wq.z, row.alpha); row.alpha = fmaf(v[j + 3], wq.w, row.alpha);
+              for (int q = 0; q < 8; ++q) {
+                uint4 o = make_uint4(pk[q * 4], pk[q * 4 + 1], pk[q * 4 + 2], pk[q * 4 + 3]);
+                *reinterpret_cast<uint4*>(blk + swz_off(r, q)) = o;
               }
             }
-            uint8_t* blk = xs + (col0 >> 6) * kABlockBytes;
-#pragma unroll
-            for (int q = 0; q < 4; ++q) store_chunk(blk, r, ((col0 & 63) >> 3) + q, v + q * 8);
           }
           if (st.write_cond)
             cond_to_block(ins, r, args.cond + row.ray * prog.cond_stride + prog.G, prog.rc);
@@ -340,7 +413,7 @@ field_tc_kernel(const __grid_constant__ TcProgram prog, const FieldArgs args,
           tmem_ld16(t_lane, v);
           tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 8; ++j) v[j] += __ldg(bias + j);
+          for (int j = 0; j < 8; ++j) v[j] += bias[j];
           if (st.epi == kEpiWarpHeads) {
             float y[3];
             if (prog.warp_type == 2) {
@@ -360,7 +433,8 @@ field_tc_kernel(const __grid_constant__ TcProgram prog, const FieldArgs args,
               const int nxt = pair + gridDim.x;
               if (nxt < num_pairs) begin_pair(nxt);
             } else {
-              posenc_to_block(ins, r, row.x, prog.Fp, nullptr, nullptr, 0);
+              if (args.fast_encode) posenc_fast_to_block(ins, r, row.x, prog.Fp, nullptr, nullptr, 0);
+              else posenc_to_block(ins, r, row.x, prog.Fp, nullptr, nullptr, 0);
             }
             arrive_both();
           } else {

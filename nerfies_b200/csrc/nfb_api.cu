@@ -305,6 +305,7 @@ int run_field(nfb_handle* h, int level, long long rows, int S, const float* orig
   a.params = h->d_packed; a.origins = origins; a.directions = directions; a.z_vals = z;
   a.cond = h->d_cond; a.window = h->d_window; a.samples = samples; a.warped = warped;
   a.num_rows = rows; a.samples_per_ray = S; a.use_warp = use_warp; a.warp_only = warp_only;
+  a.fast_encode = h->cfg.precision == NFB_PREC_BF16;
   const bool prof = h->profiling && !warp_only;
   if (prof) NFB_CUDA(cudaEventRecord(h->ev[level][0], s));
   int rc;

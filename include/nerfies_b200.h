@@ -153,6 +153,11 @@ int nfb_warp_forward(nfb_handle* h, int num_points, const float* points,
 int nfb_set_profiling(nfb_handle* h, int enabled);
 float nfb_field_time_ms(nfb_handle* h, int level);
 
+/* Debug aid: block 0 of the tensor-core field kernel appends (tag, clock64)
+ * pairs to `buffer` (device, 1 + 2*capacity int64; buffer[0] = record count,
+ * zero it first).  NULL disables tracing. */
+int nfb_set_trace(nfb_handle* h, long long* buffer, int capacity);
+
 /* Hardware self-test of the tcgen05 building blocks (UMMA descriptors, 128-byte
  * swizzle, TMEM, bulk-copy ring): C[128,N] = bf16(A[128,K]) x bf16(W[K,N]), fp32
  * accumulate.  K <= 320, N <= 256; device pointers. */

@@ -46,6 +46,8 @@ struct FieldArgs {
   int use_warp;              // run the warp net
   int warp_only;             // stop after the warp (nfb_warp_forward)
   int fast_encode;           // bf16 mode: octave-recurrence positional encoding
+  long long* trace;          // debug: (tag, clock) records of block 0, or nullptr
+  int trace_cap;
 };
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {

@@ -47,6 +47,17 @@ struct TcBars {
 };
 static_assert(sizeof(TcBars) <= 128, "barrier block");
 
+// Debug timeline: block 0 appends (tag, clock64) pairs; trace[0] is the counter.
+__device__ __forceinline__ void trace_ev(const FieldArgs& a, int role, int step, int ev) {
+  if (a.trace && blockIdx.x == 0) {
+    const unsigned long long i = atomicAdd(reinterpret_cast<unsigned long long*>(a.trace), 1ull);
+    if ((long long)i < a.trace_cap) {
+      a.trace[1 + 2 * i] = ((long long)role << 32) | ((long long)step << 8) | ev;
+      a.trace[2 + 2 * i] = clock64();
+    }
+  }
+}
+
 // Row state owned by one epilogue thread for the lifetime of a tile pair.
 struct RowState {
   float x[3];        // current (possibly warped) sample point
@@ -241,6 +252,7 @@ field_tc_kernel(const __grid_constant__ TcProgram prog, const FieldArgs args,
           const uint32_t idesc = make_idesc_bf16(kTileRows, st.chunk_n);
           mbar_wait(&bars->x_ready[0], xr & 1);
           tc_fence_after();
+          trace_ev(args, 0, si, 0);
           bool have1 = false;
           auto need1 = [&]() {
             if (!have1) { mbar_wait(&bars->x_ready[1], xr & 1); tc_fence_after(); have1 = true; }
@@ -270,6 +282,7 @@ field_tc_kernel(const __grid_constant__ TcProgram prog, const FieldArgs args,
             }
             if (c == st.n_chunks - 1) need1();   // consume x_ready[1] before the epilogue can re-arm it
             umma_commit(&bars->acc_ready[c]);
+            trace_ev(args, 0, si, 1 + c);
             if (c == 0 && st.n_chunks == 2 && st.kb_free < 0) umma_commit(&bars->x_free);
           }
           ++xr;
@@ -350,6 +363,7 @@ field_tc_kernel(const __grid_constant__ TcProgram prog, const FieldArgs args,
           uint32_t packed[64];
           mbar_wait(&bars->acc_ready[0], n_acc0++ & 1);
           tc_fence_after();
+          if (lane == 0 && (warp & 3) == 0) trace_ev(args, 1 + s, si, 0);
 #pragma unroll
           for (int pp = 0; pp < 2; ++pp) {
             if (2 * pp < np) {
@@ -361,7 +375,9 @@ field_tc_kernel(const __grid_constant__ TcProgram prog, const FieldArgs args,
               epi_piece(vb, bias + (2 * pp + 1) * 32, relu, adot, aw + (2 * pp + 1) * 32, row.alpha, packed + (2 * pp + 1) * 16);
             }
           }
+          if (lane == 0 && (warp & 3) == 0) trace_ev(args, 1 + s, si, 1);
           mbar_wait(&bars->x_free, n_free++ & 1);
+          if (lane == 0 && (warp & 3) == 0) trace_ev(args, 1 + s, si, 2);
 #pragma unroll
           for (int p = 0; p < 4; ++p) {
             if (p < np) {
@@ -377,9 +393,11 @@ field_tc_kernel(const __grid_constant__ TcProgram prog, const FieldArgs args,
           fence_proxy_async();
           tc_fence_before();
           mbar_arrive(&bars->x_ready[0]);
+          if (lane == 0 && (warp & 3) == 0) trace_ev(args, 1 + s, si, 3);
           // ---- chunk 1: every MMA of the layer is complete, store directly ----
           mbar_wait(&bars->acc_ready[1], n_acc1++ & 1);
           tc_fence_after();
+          if (lane == 0 && (warp & 3) == 0) trace_ev(args, 1 + s, si, 4);
 #pragma unroll
           for (int pp = 0; pp < 2; ++pp) {
             if (2 * pp < np) {
@@ -405,11 +423,13 @@ field_tc_kernel(const __grid_constant__ TcProgram prog, const FieldArgs args,
           fence_proxy_async();
           tc_fence_before();
           mbar_arrive(&bars->x_ready[1]);
+          if (lane == 0 && (warp & 3) == 0) trace_ev(args, 1 + s, si, 5);
         } else {
           // ---- heads: N = 16 accumulator columns, one chunk ----
           float v[16];
           mbar_wait(&bars->acc_ready[0], n_acc0++ & 1);
           tc_fence_after();
+          if (lane == 0 && (warp & 3) == 0) trace_ev(args, 1 + s, si, 0);
           tmem_ld16(t_lane, v);
           tmem_ld_wait();
 #pragma unroll
@@ -447,6 +467,7 @@ field_tc_kernel(const __grid_constant__ TcProgram prog, const FieldArgs args,
             const int nxt = pair + gridDim.x;
             if (nxt < num_pairs) begin_pair(nxt);
             arrive_both();
+            if (lane == 0 && (warp & 3) == 0) trace_ev(args, 1 + s, si, 5);
           }
         }
       }

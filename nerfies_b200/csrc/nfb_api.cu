@@ -306,6 +306,7 @@ int run_field(nfb_handle* h, int level, long long rows, int S, const float* orig
   a.cond = h->d_cond; a.window = h->d_window; a.samples = samples; a.warped = warped;
   a.num_rows = rows; a.samples_per_ray = S; a.use_warp = use_warp; a.warp_only = warp_only;
   a.fast_encode = h->cfg.precision == NFB_PREC_BF16;
+  a.trace = h->trace; a.trace_cap = h->trace_cap;
   const bool prof = h->profiling && !warp_only;
   if (prof) NFB_CUDA(cudaEventRecord(h->ev[level][0], s));
   int rc;
@@ -370,6 +371,12 @@ extern "C" {
 const char* nfb_last_error(void) { return g_error.c_str(); }
 const char* nfb_version(void) { return "nerfies_b200 0.1 sm_100a"; }
 long long nfb_kernel_launches(const nfb_handle* h) { return h ? h->launches : 0; }
+
+int nfb_set_trace(nfb_handle* h, long long* buffer, int capacity) {
+  if (!h) return fail("null handle");
+  h->trace = buffer; h->trace_cap = buffer ? capacity : 0;
+  return 0;
+}
 
 int nfb_set_profiling(nfb_handle* h, int enabled) {
   if (!h) return fail("null handle");

@@ -86,6 +86,8 @@ struct nfb_handle {
   bool ev_valid[2] = {false, false};
   int cond_stride = 0;
   int sm_count = 148;
+  long long* trace = nullptr;
+  int trace_cap = 0;
   // tensor-core path (precision != fp32)
   nfb::tc::TcProgram tcprog[2];
   unsigned char* d_wpack = nullptr;   // bf16 weight units, shared-memory image

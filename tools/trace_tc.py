@@ -1,0 +1,44 @@
+"""Timeline of the tensor-core field kernel's block 0 (GPU box)."""
+import ctypes, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import bench
+import nerfies_b200 as nb
+
+B = 8192
+model, params = nb.construct_nerf(0, bench.model_config(), B, range(200), [0], range(200), 0.02, 0.83, precision='bf16', device='cuda:0')
+rays = bench.synthetic_rays(B, 1)
+rays = {'origins': rays['origins'].cuda(), 'directions': rays['directions'].cuda(), 'metadata': {k: v.cuda() for k, v in rays['metadata'].items()}}
+out = model.apply({'params': params}, rays, warp_extra={'alpha': 8.0})
+torch.cuda.synchronize()
+hd = model.handle(B)
+cap = 20000
+buf = torch.zeros(1 + 2 * cap, dtype=torch.int64, device='cuda')
+hd.lib.nfb_set_trace(hd.h, ctypes.c_void_p(buf.data_ptr()), cap)
+from nerfies_b200 import _lib
+from nerfies_b200.models import _ptr, _stream
+z = torch.empty(B, 128, device='cuda')
+_lib.check(hd.lib.nfb_coarse_z_vals(hd.h, B, None, _ptr(z), _stream()))
+o6 = torch.empty(B, 6, device='cuda'); w = torch.empty(B, 128, device='cuda')
+ids = rays['metadata']['warp'][:, 0].contiguous(); ida = rays['metadata']['appearance'][:, 0].contiguous()
+_lib.check(hd.lib.nfb_render_samples(hd.h, 0, B, 128, _ptr(z), _ptr(rays['origins']), _ptr(rays['directions']), None, _ptr(ids), _ptr(ida), None, 8.0, 0, _ptr(o6), _ptr(w), None, None, _stream()))
+torch.cuda.synchronize()
+hd.lib.nfb_set_trace(hd.h, None, 0)
+t = buf.cpu().tolist()
+n = min(t[0], cap)
+recs = [(t[1 + 2 * i] >> 32, (t[1 + 2 * i] >> 8) & 0xffffff, t[1 + 2 * i] & 0xff, t[2 + 2 * i]) for i in range(n)]
+t0 = min(r[3] for r in recs)
+recs.sort(key=lambda r: r[3])
+names = {0: {0: 'MMA step start', 1: 'MMA chunk0 issued', 2: 'MMA chunk1 issued'},
+         1: {0: 'E0 acc0 ready', 1: 'E0 c0 math done', 2: 'E0 x_free', 3: 'E0 c0 stored', 4: 'E0 acc1 ready', 5: 'E0 step done'},
+         2: {0: 'E1 acc0 ready', 1: 'E1 c0 math done', 2: 'E1 x_free', 3: 'E1 c0 stored', 4: 'E1 acc1 ready', 5: 'E1 step done'}}
+# print the second tile pair (steady state): records 2nd occurrence of step 0 start onwards, ~130 lines
+starts = [i for i, r in enumerate(recs) if r[0] == 0 and r[1] == 0 and r[2] == 0]
+print('pairs traced:', len(starts), 'records', n)
+if len(starts) > 2:
+  a, b = starts[1], starts[2]
+  base = recs[a][3]
+  print('pair period (cycles):', recs[b][3] - recs[a][3])
+  for r in recs[a:b]:
+    if r[0] != 2:
+      print('%8d  step %2d  %s' % (r[3] - base, r[1], names[r[0]][r[2]]))

@@ -164,6 +164,11 @@ int nfb_set_trace(nfb_handle* h, long long* buffer, int capacity);
 int nfb_selftest_gemm(int K, int N, const float* A, const float* W, float* C,
                       void* stream);
 
+/* Micro-benchmark of the tensor pipe (mode 0: chain of tcgen05.mma M=128,N=n) or
+ * of TMEM reads (mode 1: tcgen05.ld by `nwarps` warps).  out (host, 3 int64):
+ * cycles, work items, issue cycles. */
+int nfb_selftest_microbench(int mode, int n, int reps, int nwarps, long long* out);
+
 /* Number of CUDA kernels this handle has launched so far (bench accounting). */
 long long nfb_kernel_launches(const nfb_handle* h);
 /* Thread-local description of the last error returned on this thread. */

@@ -15,7 +15,7 @@ SYMBOLS = [
     'nfb_set_params', 'nfb_render_forward', 'nfb_render_forward_host',
     'nfb_render_samples', 'nfb_sample_pdf', 'nfb_coarse_z_vals',
     'nfb_warp_forward', 'nfb_kernel_launches', 'nfb_last_error', 'nfb_version',
-    'nfb_set_profiling', 'nfb_field_time_ms', 'nfb_selftest_gemm', 'nfb_set_trace',
+    'nfb_set_profiling', 'nfb_field_time_ms', 'nfb_selftest_gemm', 'nfb_set_trace', 'nfb_selftest_microbench',
 ]
 
 ACTIVATIONS = {'none': 0, 'relu': 1, 'elu': 2, 'leaky_relu': 3, 'tanh': 4,
@@ -125,6 +125,8 @@ def load():
   lib.nfb_selftest_gemm.restype = ci
   lib.nfb_set_trace.argtypes = [vp, vp, ci]
   lib.nfb_set_trace.restype = ci
+  lib.nfb_selftest_microbench.argtypes = [ci, ci, ci, ci, vp]
+  lib.nfb_selftest_microbench.restype = ci
   lib.nfb_last_error.argtypes = []
   lib.nfb_last_error.restype = ctypes.c_char_p
   lib.nfb_version.argtypes = []

@@ -47,16 +47,29 @@ struct TcBars {
 };
 static_assert(sizeof(TcBars) <= 128, "barrier block");
 
-// Debug timeline: block 0 appends (tag, clock64) pairs; trace[0] is the counter.
-__device__ __forceinline__ void trace_ev(const FieldArgs& a, int role, int step, int ev) {
-  if (a.trace && blockIdx.x == 0) {
-    const unsigned long long i = atomicAdd(reinterpret_cast<unsigned long long*>(a.trace), 1ull);
-    if ((long long)i < a.trace_cap) {
-      a.trace[1 + 2 * i] = ((long long)role << 32) | ((long long)step << 8) | ev;
-      a.trace[2 + 2 * i] = clock64();
+// Debug timeline of block 0: four roles (0 MMA issuer, 1/2 epilogue of sub-tile
+// 0/1 (first lane), 3 weight producer) append (tag, clock64) pairs to private
+// regions of `trace` with plain stores; trace[role] receives the record count.
+struct Tracer {
+  long long* base;
+  int cap, n;
+  __device__ Tracer(const FieldArgs& a, int role) : base(nullptr), cap(0), n(0) {
+    if (a.trace && blockIdx.x == 0 && role >= 0) {
+      cap = a.trace_cap / 4;
+      base = a.trace + 4 + (size_t)role * cap * 2;
     }
   }
-}
+  __device__ __forceinline__ void ev(int step, int e) {
+    if (base && n < cap) {
+      base[2 * n] = ((long long)step << 8) | e;
+      base[2 * n + 1] = clock64();
+      ++n;
+    }
+  }
+  __device__ void finish(const FieldArgs& a, int role) {
+    if (base) a.trace[role] = n;
+  }
+};
 
 // Row state owned by one epilogue thread for the lifetime of a tile pair.
 struct RowState {
@@ -224,7 +237,9 @@ field_tc_kernel(const __grid_constant__ TcProgram prog, const FieldArgs args,
 
   if (warp == 9) {
     // ===================== weight producer =====================
-    if (lane == 0) {
+    // (the whole warp runs the loop; one elected lane issues the copies)
+    {
+      Tracer tr(args, lane == 0 ? 3 : -1);
       uint32_t it = 0;
       for (int pair = blockIdx.x; pair < num_pairs; pair += gridDim.x) {
         for (int si = first_step; si <= last_step; ++si) {
@@ -235,15 +250,22 @@ field_tc_kernel(const __grid_constant__ TcProgram prog, const FieldArgs args,
             const int sg = it % kStages;
             const uint32_t ph = (it / kStages) & 1;
             mbar_wait(&bars->empty[sg], ph ^ 1);
-            mbar_arrive_expect_tx(&bars->full[sg], bytes);
-            bulk_g2s(stages + sg * kStageBytes, src + (size_t)u * bytes, bytes, &bars->full[sg]);
+            tr.ev(si, u);
+            if (elect_one()) {
+              mbar_arrive_expect_tx(&bars->full[sg], bytes);
+              bulk_g2s(stages + sg * kStageBytes, src + (size_t)u * bytes, bytes, &bars->full[sg]);
+            }
+            __syncwarp();
           }
         }
       }
+      if (lane == 0) tr.finish(args, 3);
     }
   } else if (warp == 8) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // Warp-uniform control flow; tcgen05.mma / commit issued by one elected lane.
+    {
+      Tracer tr(args, lane == 0 ? 0 : -1);
       uint32_t it = 0, xr = 0;
       int prev_split = 99;   // first activation block produced by chunk 1 of the previous step
       for (int pair = blockIdx.x; pair < num_pairs; pair += gridDim.x) {
@@ -252,7 +274,7 @@ field_tc_kernel(const __grid_constant__ TcProgram prog, const FieldArgs args,
           const uint32_t idesc = make_idesc_bf16(kTileRows, st.chunk_n);
           mbar_wait(&bars->x_ready[0], xr & 1);
           tc_fence_after();
-          trace_ev(args, 0, si, 0);
+          tr.ev(si, 0);
           bool have1 = false;
           auto need1 = [&]() {
             if (!have1) { mbar_wait(&bars->x_ready[1], xr & 1); tc_fence_after(); have1 = true; }
@@ -263,32 +285,41 @@ field_tc_kernel(const __grid_constant__ TcProgram prog, const FieldArgs args,
               const int b = st.src[kb];
               if (b < kSrcIn && b >= prev_split) need1();
               const int sg = it % kStages;
+              tr.ev(si, 10 + c * 8 + kb);
               mbar_wait(&bars->full[sg], (it / kStages) & 1);
               tc_fence_after();
+              tr.ev(si, 30 + c * 8 + kb);
               const uint32_t b_addr = smem_u32(stages + sg * kStageBytes);
+              if (elect_one()) {
 #pragma unroll
-              for (int s = 0; s < 2; ++s) {
-                const uint8_t* a_ptr = (b < kSrcIn) ? xbuf + (s * 4 + b) * kABlockBytes
-                                                    : inbuf + s * kABlockBytes;
-                const uint32_t a_addr = smem_u32(a_ptr);
-                const uint32_t d = tmem_base + s * 256 + c * st.chunk_n;
+                for (int s = 0; s < 2; ++s) {
+                  const uint8_t* a_ptr = (b < kSrcIn) ? xbuf + (s * 4 + b) * kABlockBytes
+                                                      : inbuf + s * kABlockBytes;
+                  const uint32_t a_addr = smem_u32(a_ptr);
+                  const uint32_t d = tmem_base + s * 256 + c * st.chunk_n;
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
-                  umma_bf16(d, make_smem_desc(a_addr + k * 32), make_smem_desc(b_addr + k * 32),
-                            idesc, (kb | k) ? 1u : 0u);
+                  for (int k = 0; k < 4; ++k)
+                    umma_bf16(d, make_smem_desc(a_addr + k * 32), make_smem_desc(b_addr + k * 32),
+                              idesc, (kb | k) ? 1u : 0u);
+                }
+                umma_commit(&bars->empty[sg]);
+                if (c == 1 && kb == st.kb_free) umma_commit(&bars->x_free);
               }
-              umma_commit(&bars->empty[sg]);
-              if (c == 1 && kb == st.kb_free) umma_commit(&bars->x_free);
+              __syncwarp();
             }
             if (c == st.n_chunks - 1) need1();   // consume x_ready[1] before the epilogue can re-arm it
-            umma_commit(&bars->acc_ready[c]);
-            trace_ev(args, 0, si, 1 + c);
-            if (c == 0 && st.n_chunks == 2 && st.kb_free < 0) umma_commit(&bars->x_free);
+            if (elect_one()) {
+              umma_commit(&bars->acc_ready[c]);
+              if (c == 0 && st.n_chunks == 2 && st.kb_free < 0) umma_commit(&bars->x_free);
+            }
+            __syncwarp();
+            tr.ev(si, 1 + c);
           }
           ++xr;
           prev_split = (st.n_chunks == 2) ? st.chunk_n / kBlockK : 99;
         }
       }
+      if (lane == 0) tr.finish(args, 0);
     }
   } else {
     // ===================== epilogue: one thread per row =====================
@@ -297,6 +328,7 @@ field_tc_kernel(const __grid_constant__ TcProgram prog, const FieldArgs args,
     const uint32_t t_lane = tmem_base + (((uint32_t)(warp & 3) * 32) << 16) + s * 256;
     uint8_t* xs = xbuf + s * 4 * kABlockBytes;
     uint8_t* ins = inbuf + s * kABlockBytes;
+    Tracer tr(args, (lane == 0 && (warp & 3) == 0) ? 1 + s : -1);
     uint32_t n_acc0 = 0, n_acc1 = 0, n_free = 0, n_step = 0;
     float next_bias = __ldg(aux + prog.steps[first_step].b_off + tid);
     RowState row;
@@ -363,7 +395,7 @@ field_tc_kernel(const __grid_constant__ TcProgram prog, const FieldArgs args,
           uint32_t packed[64];
           mbar_wait(&bars->acc_ready[0], n_acc0++ & 1);
           tc_fence_after();
-          if (lane == 0 && (warp & 3) == 0) trace_ev(args, 1 + s, si, 0);
+          tr.ev(si, 0);
 #pragma unroll
           for (int pp = 0; pp < 2; ++pp) {
             if (2 * pp < np) {
@@ -375,9 +407,9 @@ field_tc_kernel(const __grid_constant__ TcProgram prog, const FieldArgs args,
               epi_piece(vb, bias + (2 * pp + 1) * 32, relu, adot, aw + (2 * pp + 1) * 32, row.alpha, packed + (2 * pp + 1) * 16);
             }
           }
-          if (lane == 0 && (warp & 3) == 0) trace_ev(args, 1 + s, si, 1);
+          tr.ev(si, 1);
           mbar_wait(&bars->x_free, n_free++ & 1);
-          if (lane == 0 && (warp & 3) == 0) trace_ev(args, 1 + s, si, 2);
+          tr.ev(si, 2);
 #pragma unroll
           for (int p = 0; p < 4; ++p) {
             if (p < np) {
@@ -393,11 +425,11 @@ field_tc_kernel(const __grid_constant__ TcProgram prog, const FieldArgs args,
           fence_proxy_async();
           tc_fence_before();
           mbar_arrive(&bars->x_ready[0]);
-          if (lane == 0 && (warp & 3) == 0) trace_ev(args, 1 + s, si, 3);
+          tr.ev(si, 3);
           // ---- chunk 1: every MMA of the layer is complete, store directly ----
           mbar_wait(&bars->acc_ready[1], n_acc1++ & 1);
           tc_fence_after();
-          if (lane == 0 && (warp & 3) == 0) trace_ev(args, 1 + s, si, 4);
+          tr.ev(si, 4);
 #pragma unroll
           for (int pp = 0; pp < 2; ++pp) {
             if (2 * pp < np) {
@@ -423,13 +455,13 @@ field_tc_kernel(const __grid_constant__ TcProgram prog, const FieldArgs args,
           fence_proxy_async();
           tc_fence_before();
           mbar_arrive(&bars->x_ready[1]);
-          if (lane == 0 && (warp & 3) == 0) trace_ev(args, 1 + s, si, 5);
+          tr.ev(si, 5);
         } else {
           // ---- heads: N = 16 accumulator columns, one chunk ----
           float v[16];
           mbar_wait(&bars->acc_ready[0], n_acc0++ & 1);
           tc_fence_after();
-          if (lane == 0 && (warp & 3) == 0) trace_ev(args, 1 + s, si, 0);
+          tr.ev(si, 0);
           tmem_ld16(t_lane, v);
           tmem_ld_wait();
 #pragma unroll
@@ -467,11 +499,12 @@ field_tc_kernel(const __grid_constant__ TcProgram prog, const FieldArgs args,
             const int nxt = pair + gridDim.x;
             if (nxt < num_pairs) begin_pair(nxt);
             arrive_both();
-            if (lane == 0 && (warp & 3) == 0) trace_ev(args, 1 + s, si, 5);
+            tr.ev(si, 5);
           }
         }
       }
     }
+    tr.finish(args, 1 + s);
     tc_fence_before();
   }
   __syncthreads();

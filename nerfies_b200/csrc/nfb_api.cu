@@ -425,6 +425,22 @@ int nfb_selftest_gemm(int K, int N, const float* A, const float* W, float* C, vo
   return 0;
 }
 
+int nfb_selftest_microbench(int mode, int n, int reps, int nwarps, long long* out) {
+  using namespace nfb::tc;
+  if (!out || n < 16 || n > 256 || n % 16) return fail("microbench: bad arguments");
+  long long* d = nullptr;
+  NFB_CUDA(cudaMalloc(&d, 4 * sizeof(long long)));
+  NFB_CUDA(cudaMemset(d, 0, 4 * sizeof(long long)));
+  const int smem = kABlockBytes + 256 * kRowBytes;
+  NFB_CUDA(cudaFuncSetAttribute(tc_microbench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  tc_microbench_kernel<<<1, 288, smem>>>(mode, n, reps, nwarps, d);
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e == cudaSuccess) e = cudaMemcpy(out, d, 3 * sizeof(long long), cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  if (e != cudaSuccess) return fail("microbench failed: %s", cudaGetErrorString(e));
+  return 0;
+}
+
 int nfb_create(const nfb_config* cfg, int max_rays, nfb_handle** out) {
   if (!cfg || !out) return fail("null argument");
   if (max_rays < 1) return fail("max_rays must be >= 1");

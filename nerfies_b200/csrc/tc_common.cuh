@@ -31,6 +31,20 @@ __device__ __host__ __forceinline__ uint32_t swz_off(int row, int chunk) {
   return (uint32_t)(row * kRowBytes + ((chunk ^ (row & 7)) << 4));
 }
 
+// Warp-uniform leader election (elect.sync).  Control flow stays uniform for the
+// whole warp, so the compiler keeps descriptors in uniform registers instead of
+// wrapping every tcgen05 instruction in a divergence "waterfall" loop.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
+      "elect.sync rx|px, %1;\n\t"
+      "selp.u32 %0, 1, 0, px;\n\t}"
+      : "=r"(pred)
+      : "r"(0xffffffffu));
+  return pred != 0;
+}
+
 // ---- mbarrier ----------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));

@@ -103,3 +103,73 @@ tc_selftest_kernel(const float* __restrict__ A, int K, const __nv_bfloat16* __re
 
 }  // namespace tc
 }  // namespace nfb
+
+// ---------------------------------------------------------------------------
+// Micro-benchmarks of the two rates that bound the fused kernel:
+//   mode 0: a chain of `reps` x 4 tcgen05.mma (M=128, N=n, K=16, SS operands
+//           resident in shared memory) - cycles from first issue to completion;
+//   mode 1: `reps` x (two tcgen05.ld 32x32b.x32 + wait) by 4 or 8 warps -
+//           cycles seen by warp 0.
+// out[0] = cycles, out[1] = work items (MMAs or 32-column loads per warp).
+// ---------------------------------------------------------------------------
+namespace nfb {
+namespace tc {
+
+__global__ void __launch_bounds__(288, 1)
+tc_microbench_kernel(int mode, int n, int reps, int nwarps, long long* out) {
+  extern __shared__ __align__(1024) uint8_t raw[];
+  uint8_t* a_blk = raw;                       // 16 KB
+  uint8_t* b_blk = raw + kABlockBytes;        // up to 32 KB
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_slot;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (int i = tid; i < (kABlockBytes + 256 * kRowBytes) / 4; i += blockDim.x)
+    reinterpret_cast<uint32_t*>(raw)[i] = 0x3c003c00u;   // small bf16 values
+  if (tid == 256) { mbar_init(&bar, 1); fence_barrier_init(); }
+  if (warp == 8) tmem_alloc(&tmem_slot, 512);
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+  if (mode == 0) {
+    if (tid == 256) {
+      const uint32_t idesc = make_idesc_bf16(128, n);
+      const uint32_t a = smem_u32(a_blk), b = smem_u32(b_blk);
+      const long long t0 = clock64();
+      for (int r = 0; r < reps; ++r) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_bf16(tmem_base + (r & 1) * 256, make_smem_desc(a + k * 32), make_smem_desc(b + k * 32), idesc, 1u);
+      }
+      umma_commit(&bar);
+      const long long t1 = clock64();
+      mbar_wait(&bar, 0);
+      const long long t2 = clock64();
+      out[0] = t2 - t0; out[1] = 4LL * reps; out[2] = t1 - t0;
+    }
+  } else {
+    if (warp < nwarps) {
+      const uint32_t t_lane = tmem_base + (((uint32_t)(warp & 3) * 32) << 16) + (warp >> 2) * 256;
+      float acc = 0.f;
+      const long long t0 = clock64();
+      for (int r = 0; r < reps; ++r) {
+        float va[32], vb[32];
+        tmem_ld32(t_lane + (r & 3) * 64, va);
+        tmem_ld32(t_lane + (r & 3) * 64 + 32, vb);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) acc += va[j] + vb[j];
+      }
+      const long long t1 = clock64();
+      if (tid == 0) { out[0] = t1 - t0; out[1] = 2LL * reps; }
+      if (acc == 123.456f) out[3] = 1;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) tmem_dealloc(tmem_base, 512);
+}
+
+}  // namespace tc
+}  // namespace nfb

@@ -1,0 +1,15 @@
+import ctypes, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from nerfies_b200 import _lib
+lib = _lib.load()
+torch.zeros(1).cuda()
+out = (ctypes.c_longlong * 3)()
+for n in (64, 128, 256):
+  for reps in (64, 512):
+    _lib.check(lib.nfb_selftest_microbench(0, n, reps, 0, out))
+    print(f'MMA M=128 N={n} K=16 SS: {out[0]/out[1]:.1f} cycles/MMA over {out[1]} MMAs (issue {out[2]/out[1]:.1f}/MMA)')
+for nw in (1, 4, 8):
+  _lib.check(lib.nfb_selftest_microbench(1, 128, 256, nw, out))
+  per = out[0] / out[1]
+  print(f'LDTM 32x32b.x32 by {nw} warps: {per:.1f} cycles per 4 KB load per warp -> {nw*4096/per:.0f} B/clk/SM')

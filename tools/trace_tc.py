@@ -13,7 +13,7 @@ out = model.apply({'params': params}, rays, warp_extra={'alpha': 8.0})
 torch.cuda.synchronize()
 hd = model.handle(B)
 cap = 20000
-buf = torch.zeros(1 + 2 * cap, dtype=torch.int64, device='cuda')
+buf = torch.zeros(4 + 2 * cap, dtype=torch.int64, device='cuda')
 hd.lib.nfb_set_trace(hd.h, ctypes.c_void_p(buf.data_ptr()), cap)
 from nerfies_b200 import _lib
 from nerfies_b200.models import _ptr, _stream
@@ -25,8 +25,13 @@ _lib.check(hd.lib.nfb_render_samples(hd.h, 0, B, 128, _ptr(z), _ptr(rays['origin
 torch.cuda.synchronize()
 hd.lib.nfb_set_trace(hd.h, None, 0)
 t = buf.cpu().tolist()
-n = min(t[0], cap)
-recs = [(t[1 + 2 * i] >> 32, (t[1 + 2 * i] >> 8) & 0xffffff, t[1 + 2 * i] & 0xff, t[2 + 2 * i]) for i in range(n)]
+per = cap // 4
+recs = []
+for role in range(4):
+  for i in range(min(t[role], per)):
+    tag, clk = t[4 + role * per * 2 + 2 * i], t[4 + role * per * 2 + 2 * i + 1]
+    recs.append((role, tag >> 8, tag & 0xff, clk))
+n = len(recs)
 t0 = min(r[3] for r in recs)
 recs.sort(key=lambda r: r[3])
 names = {0: {0: 'MMA step start', 1: 'MMA chunk0 issued', 2: 'MMA chunk1 issued'},
@@ -39,6 +44,11 @@ if len(starts) > 2:
   a, b = starts[1], starts[2]
   base = recs[a][3]
   print('pair period (cycles):', recs[b][3] - recs[a][3])
+  lo, hi = int(os.environ.get('STEP_LO', '8')), int(os.environ.get('STEP_HI', '10'))
   for r in recs[a:b]:
-    if r[0] != 2:
-      print('%8d  step %2d  %s' % (r[3] - base, r[1], names[r[0]][r[2]]))
+    if lo <= r[1] <= hi:
+      if r[0] == 3: nm = 'PROD copy issued unit %d' % r[2]
+      elif r[0] == 0 and r[2] >= 30: nm = 'MMA  got weights c%d kb%d' % ((r[2] - 30) // 8, (r[2] - 30) % 8)
+      elif r[0] == 0 and r[2] >= 10: nm = 'MMA  wait weights c%d kb%d' % ((r[2] - 10) // 8, (r[2] - 10) % 8)
+      else: nm = names[r[0]][r[2]]
+      print('%8d  step %2d  %s' % (r[3] - base, r[1], nm))

@@ -263,60 +263,85 @@ field_tc_kernel(const __grid_constant__ TcProgram prog, const FieldArgs args,
     }
   } else if (warp == 8) {
     // ===================== MMA issuer =====================
-    // Warp-uniform control flow; tcgen05.mma / commit issued by one elected lane.
+    // Warp-uniform outer control flow; inside a chunk one elected lane issues all
+    // tcgen05.mma / commits and probes the next weight unit's barrier while the
+    // current unit's last MMAs are still being queued (the tensor queue is
+    // shallow: any gap between bursts idles the pipe).
     {
       Tracer tr(args, lane == 0 ? 0 : -1);
       uint32_t it = 0, xr = 0;
       int prev_split = 99;   // first activation block produced by chunk 1 of the previous step
+      const uint64_t desc_hi = make_smem_desc(0);             // layout/SBO/version bits
+      const uint32_t x_lo = (smem_u32(xbuf) & 0x3FFFFu) >> 4;
+      const uint32_t in_lo = (smem_u32(inbuf) & 0x3FFFFu) >> 4;
+      const uint32_t st_lo = (smem_u32(stages) & 0x3FFFFu) >> 4;
       for (int pair = blockIdx.x; pair < num_pairs; pair += gridDim.x) {
         for (int si = first_step; si <= last_step; ++si) {
           const TcStep& st = prog.steps[si];
-          const uint32_t idesc = make_idesc_bf16(kTileRows, st.chunk_n);
+          // step fields -> registers (constant-bank loads off the issue path)
+          const int nkb = st.nkb, nch = st.n_chunks, chunk_n = st.chunk_n, kb_free = st.kb_free;
+          uint32_t srcs = 0;
+          for (int kb = 0; kb < nkb; ++kb) srcs |= (uint32_t)st.src[kb] << (4 * kb);
+          // first K-block that reads an activation block written by chunk 1 of the
+          // previous step (needs x_ready[1]); sources are [IN?, 0, 1, 2, 3].
+          int kb_need = nkb;
+          for (int kb = nkb - 1; kb >= 0; --kb) {
+            const int b = (srcs >> (4 * kb)) & 15;
+            if (b < kSrcIn && b >= prev_split) kb_need = kb;
+          }
+          const uint32_t idesc = make_idesc_bf16(kTileRows, chunk_n);
           mbar_wait(&bars->x_ready[0], xr & 1);
           tc_fence_after();
           tr.ev(si, 0);
           bool have1 = false;
-          auto need1 = [&]() {
-            if (!have1) { mbar_wait(&bars->x_ready[1], xr & 1); tc_fence_after(); have1 = true; }
-          };
-          for (int c = 0; c < st.n_chunks; ++c) {
-            if (c == 1) need1();          // chunk-1 accumulator columns must be drained
-            for (int kb = 0; kb < st.nkb; ++kb, ++it) {
-              const int b = st.src[kb];
-              if (b < kSrcIn && b >= prev_split) need1();
-              const int sg = it % kStages;
-              tr.ev(si, 10 + c * 8 + kb);
-              mbar_wait(&bars->full[sg], (it / kStages) & 1);
-              tc_fence_after();
-              tr.ev(si, 30 + c * 8 + kb);
-              const uint32_t b_addr = smem_u32(stages + sg * kStageBytes);
+          for (int c = 0; c < nch; ++c) {
+            if (c == 1 && !have1) { mbar_wait(&bars->x_ready[1], xr & 1); tc_fence_after(); have1 = true; }
+            for (int seg = 0; seg < 2; ++seg) {
+              const int kb0 = seg == 0 ? 0 : (have1 ? nkb : kb_need);
+              const int kb1 = seg == 0 ? (have1 ? nkb : kb_need) : nkb;
+              if (seg == 1 && kb0 < kb1) { mbar_wait(&bars->x_ready[1], xr & 1); tc_fence_after(); have1 = true; }
+              if (kb0 >= kb1) continue;
+              const uint32_t it0 = it;
+              it += (uint32_t)(kb1 - kb0);        // every lane keeps the unit counter
               if (elect_one()) {
-#pragma unroll
-                for (int s = 0; s < 2; ++s) {
-                  const uint8_t* a_ptr = (b < kSrcIn) ? xbuf + (s * 4 + b) * kABlockBytes
-                                                      : inbuf + s * kABlockBytes;
-                  const uint32_t a_addr = smem_u32(a_ptr);
-                  const uint32_t d = tmem_base + s * 256 + c * st.chunk_n;
-#pragma unroll
-                  for (int k = 0; k < 4; ++k)
-                    umma_bf16(d, make_smem_desc(a_addr + k * 32), make_smem_desc(b_addr + k * 32),
-                              idesc, (kb | k) ? 1u : 0u);
+                uint32_t it = it0;
+                bool ready = mbar_test(&bars->full[it % kStages], (it / kStages) & 1);
+                for (int kb = kb0; kb < kb1; ++kb, ++it) {
+                  const int sg = it % kStages;
+                  if (!ready) mbar_wait(&bars->full[sg], (it / kStages) & 1);
+                  tc_fence_after();
+                  const int b = (srcs >> (4 * kb)) & 15;
+                  const uint64_t bd = desc_hi | (uint64_t)(st_lo + sg * (kStageBytes >> 4));
+                  const uint32_t a0 = (b < kSrcIn) ? x_lo + b * (kABlockBytes >> 4) : in_lo;
+                  const uint32_t a1 = (b < kSrcIn) ? a0 + 4 * (kABlockBytes >> 4) : in_lo + (kABlockBytes >> 4);
+                  const uint64_t ad0 = desc_hi | (uint64_t)a0, ad1 = desc_hi | (uint64_t)a1;
+                  const uint32_t d0 = tmem_base + c * chunk_n, d1 = d0 + 256;
+                  umma_bf16(d0, ad0, bd, idesc, kb ? 1u : 0u);
+                  umma_bf16(d0, ad0 + 2, bd + 2, idesc, 1u);
+                  umma_bf16(d0, ad0 + 4, bd + 4, idesc, 1u);
+                  umma_bf16(d0, ad0 + 6, bd + 6, idesc, 1u);
+                  umma_bf16(d1, ad1, bd, idesc, kb ? 1u : 0u);
+                  umma_bf16(d1, ad1 + 2, bd + 2, idesc, 1u);
+                  // look ahead while the last MMAs of this unit are queued
+                  ready = (kb + 1 < kb1) && mbar_test(&bars->full[(it + 1) % kStages], ((it + 1) / kStages) & 1);
+                  umma_bf16(d1, ad1 + 4, bd + 4, idesc, 1u);
+                  umma_bf16(d1, ad1 + 6, bd + 6, idesc, 1u);
+                  umma_commit(&bars->empty[sg]);
+                  if (c == 1 && kb == kb_free) umma_commit(&bars->x_free);
                 }
-                umma_commit(&bars->empty[sg]);
-                if (c == 1 && kb == st.kb_free) umma_commit(&bars->x_free);
               }
               __syncwarp();
             }
-            if (c == st.n_chunks - 1) need1();   // consume x_ready[1] before the epilogue can re-arm it
+            if (c == nch - 1 && !have1) { mbar_wait(&bars->x_ready[1], xr & 1); tc_fence_after(); have1 = true; }
             if (elect_one()) {
               umma_commit(&bars->acc_ready[c]);
-              if (c == 0 && st.n_chunks == 2 && st.kb_free < 0) umma_commit(&bars->x_free);
+              if (c == 0 && nch == 2 && kb_free < 0) umma_commit(&bars->x_free);
             }
             __syncwarp();
             tr.ev(si, 1 + c);
           }
           ++xr;
-          prev_split = (st.n_chunks == 2) ? st.chunk_n / kBlockK : 99;
+          prev_split = (nch == 2) ? chunk_n / kBlockK : 99;
         }
       }
       if (lane == 0) tr.finish(args, 0);
@@ -542,8 +567,10 @@ inline int build_tc_program(nfb_handle* h, int level, long long* wbytes, long lo
     if (st.k_x % kBlockK || st.k_x > 256 || st.k_in > kBlockK) return tc_fail("layer widths must be multiples of 64 (<= 256)");
     if (st.k_x && st.k_x != cur_width) return tc_fail("unexpected layer input width");
     t.nkb = 0;
-    for (int b = 0; b < st.k_x / kBlockK; ++b) t.src[t.nkb++] = b;
+    // The input block is never rewritten between a step's producer and consumer,
+    // so it goes first: its MMAs can issue before the previous epilogue is done.
     if (st.k_in) t.src[t.nkb++] = kSrcIn;
+    for (int b = 0; b < st.k_x / kBlockK; ++b) t.src[t.nkb++] = b;
     t.epi = epi;
     if (epi == kEpiHidden) {
       if (st.n != 128 && st.n != 256) return tc_fail("hidden widths must be 128 or 256");

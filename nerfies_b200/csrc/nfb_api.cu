@@ -429,12 +429,16 @@ int nfb_selftest_microbench(int mode, int n, int reps, int nwarps, long long* ou
   using namespace nfb::tc;
   if (!out || n < 16 || n > 256 || n % 16) return fail("microbench: bad arguments");
   long long* d = nullptr;
+  unsigned char* g = nullptr;
   NFB_CUDA(cudaMalloc(&d, 4 * sizeof(long long)));
   NFB_CUDA(cudaMemset(d, 0, 4 * sizeof(long long)));
-  const int smem = kABlockBytes + 256 * kRowBytes;
+  NFB_CUDA(cudaMalloc(&g, 16384));
+  NFB_CUDA(cudaMemset(g, 0, 16384));
+  const int smem = 7 * 16384;
   NFB_CUDA(cudaFuncSetAttribute(tc_microbench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  tc_microbench_kernel<<<1, 288, smem>>>(mode, n, reps, nwarps, d);
+  tc_microbench_kernel<<<1, 320, smem>>>(mode, n, reps, nwarps, d, g);
   cudaError_t e = cudaDeviceSynchronize();
+  cudaFree(g);
   if (e == cudaSuccess) e = cudaMemcpy(out, d, 3 * sizeof(long long), cudaMemcpyDeviceToHost);
   cudaFree(d);
   if (e != cudaSuccess) return fail("microbench failed: %s", cudaGetErrorString(e));

@@ -115,38 +115,119 @@ tc_selftest_kernel(const float* __restrict__ A, int K, const __nv_bfloat16* __re
 namespace nfb {
 namespace tc {
 
-__global__ void __launch_bounds__(288, 1)
-tc_microbench_kernel(int mode, int n, int reps, int nwarps, long long* out) {
-  extern __shared__ __align__(1024) uint8_t raw[];
+__global__ void __launch_bounds__(320, 1)
+tc_microbench_kernel(int mode, int n, int reps, int nwarps, long long* out, const uint8_t* gsrc) {
+  extern __shared__ __align__(1024) uint8_t raw[];   // 7 x 16 KB: A (2 half-blocks), B stages 1..4, scratch
   uint8_t* a_blk = raw;                       // 16 KB
   uint8_t* b_blk = raw + kABlockBytes;        // up to 32 KB
-  __shared__ uint64_t bar;
+  __shared__ uint64_t bar, bar2, bar3, bar4;
   __shared__ uint32_t tmem_slot;
+  __shared__ volatile int stop_flag;
   const int tid = threadIdx.x, warp = tid >> 5;
-  for (int i = tid; i < (kABlockBytes + 256 * kRowBytes) / 4; i += blockDim.x)
+  if (tid == 0) stop_flag = 0;
+  for (int i = tid; i < 7 * 16384 / 4; i += blockDim.x)
     reinterpret_cast<uint32_t*>(raw)[i] = 0x3c003c00u;   // small bf16 values
-  if (tid == 256) { mbar_init(&bar, 1); fence_barrier_init(); }
+  if (tid == 256) { mbar_init(&bar, 1); mbar_init(&bar2, 1 << 20); mbar_init(&bar3, 1); mbar_init(&bar4, 1); fence_barrier_init(); }
   if (warp == 8) tmem_alloc(&tmem_slot, 512);
   fence_proxy_async();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
-  if (mode == 0) {
-    if (tid == 256) {
+  if (mode == 2) {
+    // The fused kernel's issue loop verbatim: whole warp in the loop, per unit a
+    // wait on an (already complete) mbarrier + tcgen05.fence::after_thread_sync,
+    // then 8 MMAs + commit by one elected lane.  nwarps = variant mask:
+    //  bit0: skip the fence, bit1: skip the wait, bit2: commit to the scratch barrier
+    //  bit3: B cycles through 4 x 16 KB stages, bit4: warp 9 streams bulk copies
+    //  into a scratch stage meanwhile, bit5: warps 0-7 run tcgen05.ld loops meanwhile
+    if (warp == 9 && (nwarps & 16)) {
+      uint8_t* scratch = raw + 6 * 16384;
+      uint32_t ph = 0;
+      while (!stop_flag) {
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&bar4, 16384);
+          bulk_g2s(scratch, gsrc, 16384, &bar4);
+        }
+        __syncwarp();
+        mbar_wait(&bar4, ph);
+        ph ^= 1;
+      }
+    }
+    if (warp < 8 && (nwarps & 32)) {
+      const uint32_t t_lane = tmem_base + (((uint32_t)(warp & 3) * 32) << 16) + (warp >> 2) * 256;
+      float acc = 0.f;
+      while (!stop_flag) {
+        float va[32], vb[32];
+        tmem_ld32(t_lane + 128, va);
+        tmem_ld32(t_lane + 160, vb);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) acc += va[j] + vb[j];
+      }
+      if (acc == 123.456f) out[3] = 1;
+    }
+    if (warp == 8) {
       const uint32_t idesc = make_idesc_bf16(128, n);
       const uint32_t a = smem_u32(a_blk), b = smem_u32(b_blk);
       const long long t0 = clock64();
       for (int r = 0; r < reps; ++r) {
+        if (!(nwarps & 2)) mbar_wait(&bar3, 1);
+        if (!(nwarps & 1)) tc_fence_after();
+        const uint32_t b_r = (nwarps & 8) ? b + (r & 3) * 16384 : b;
+        if (elect_one()) {
+#pragma unroll
+          for (int s2 = 0; s2 < 2; ++s2)
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_bf16(tmem_base + s2 * 256, make_smem_desc(a + s2 * 8192 + k * 32), make_smem_desc(b_r + k * 32), idesc, 1u);
+          if (nwarps & 4) umma_commit(&bar2);
+        }
+        __syncwarp();
+      }
+      if (elect_one()) umma_commit(&bar);
+      __syncwarp();
+      const long long t1 = clock64();
+      mbar_wait(&bar, 0);
+      const long long t2 = clock64();
+      if (tid == 256) { out[0] = t2 - t0; out[1] = 8LL * reps; out[2] = t1 - t0; }
+      stop_flag = 1;
+    }
+  } else if (mode == 0) {
+    if (tid == 256) {
+      const uint32_t idesc = make_idesc_bf16(128, n);
+      const uint32_t a = smem_u32(a_blk), b = smem_u32(b_blk);
+      // nwarps doubles as a variant mask in mode 0:
+      //  bit0: commit (to a scratch barrier) after every 8 MMAs
+      //  bit1: alternate the A block / accumulator every 4 MMAs (two sub-tiles)
+      //  bit2: 8 other warps generate shared-memory load/store traffic meanwhile
+      const int variant = nwarps;
+      const long long t0 = clock64();
+      for (int r = 0; r < reps; ++r) {
+        const uint32_t a_r = (variant & 2) ? a + (r & 1) * 8192 : a;
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-          umma_bf16(tmem_base + (r & 1) * 256, make_smem_desc(a + k * 32), make_smem_desc(b + k * 32), idesc, 1u);
+          umma_bf16(tmem_base + (r & 1) * 256, make_smem_desc(a_r + k * 32), make_smem_desc(b + k * 32), idesc, 1u);
+        if ((variant & 1) && (r & 1)) umma_commit(&bar2);
       }
       umma_commit(&bar);
       const long long t1 = clock64();
       mbar_wait(&bar, 0);
       const long long t2 = clock64();
       out[0] = t2 - t0; out[1] = 4LL * reps; out[2] = t1 - t0;
+      stop_flag = 1;
+    } else if (warp < 8 && (nwarps & 4)) {
+      // epilogue-like traffic: 128-bit swizzled stores + broadcast loads
+      uint8_t* scratch = b_blk + 128 * kRowBytes;   // upper half of the B region (unused for n<=128)
+      float acc = 0.f;
+      while (!stop_flag) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          *reinterpret_cast<uint4*>(scratch + swz_off(tid & 127, q)) = make_uint4(tid, q, 0, 0);
+          acc += *reinterpret_cast<volatile float*>(scratch + q * 16);
+        }
+      }
+      if (acc == 123.456f) out[3] = 1;
     }
   } else {
     if (warp < nwarps) {

@@ -9,6 +9,12 @@ for n in (64, 128, 256):
   for reps in (64, 512):
     _lib.check(lib.nfb_selftest_microbench(0, n, reps, 0, out))
     print(f'MMA M=128 N={n} K=16 SS: {out[0]/out[1]:.1f} cycles/MMA over {out[1]} MMAs (issue {out[2]/out[1]:.1f}/MMA)')
+for variant in (1, 2, 3, 4, 7):
+  _lib.check(lib.nfb_selftest_microbench(0, 128, 512, variant, out))
+  print(f'MMA N=128 variant {variant:03b} (bit0 commit/8, bit1 alt A+D, bit2 smem traffic): {out[0]/out[1]:.1f} cycles/MMA')
+for variant in (4, 12, 20, 36, 60):
+  _lib.check(lib.nfb_selftest_microbench(2, 128, 512, variant, out))
+  print(f'issue-loop N=128 variant {variant:06b} (b2 commit/unit, b3 B cycles 4 stages, b4 concurrent bulk copies, b5 concurrent LDTM x8 warps): {out[0]/out[1]:.1f} cycles/MMA')
 for nw in (1, 4, 8):
   _lib.check(lib.nfb_selftest_microbench(1, 128, 256, nw, out))
   per = out[0] / out[1]

@@ -447,6 +447,10 @@ field_tc_kernel(const __grid_constant__ TcProgram prog, const FieldArgs args,
               }
             }
           }
+          // The input block is the first K-block of the next step (read right after
+          // x_ready[0]); every earlier reader of it (the skip layer) is complete.
+          if (st.write_cond)
+            cond_to_block(ins, r, args.cond + row.ray * prog.cond_stride + prog.G, prog.rc);
           fence_proxy_async();
           tc_fence_before();
           mbar_arrive(&bars->x_ready[0]);
@@ -475,8 +479,6 @@ field_tc_kernel(const __grid_constant__ TcProgram prog, const FieldArgs args,
               }
             }
           }
-          if (st.write_cond)
-            cond_to_block(ins, r, args.cond + row.ray * prog.cond_stride + prog.G, prog.rc);
           fence_proxy_async();
           tc_fence_before();
           mbar_arrive(&bars->x_ready[1]);

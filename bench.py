@@ -155,19 +155,32 @@ def time_oracle(num_rays, threads, seed=0):
   return time.perf_counter() - t0
 
 
+def best_thread_count():
+  """torch's intra-op pool does not scale to every core on large hosts (128
+  threads on the GPU box is ~30x slower than 8-32): probe a few counts on a small
+  sample and keep the fastest.  Returns (threads, rays_per_second)."""
+  cores = os.cpu_count() or 1
+  cands = sorted({c for c in (cores, 64, 32, 16, 8) if c <= cores})
+  time_oracle(128, cands[0])                     # warm-up (thread pools, MKL)
+  best = None
+  for c in cands:
+    t = time_oracle(128, c)
+    if best is None or t < best[1]:
+      best = (c, t)
+  return best[0], 128 / best[1]
+
+
 def cpu_baseline(budget_s):
   """The reference's algorithm on the host cores (oracle port; the JAX original
   cannot run in this image), on a bounded sample of the same workload."""
-  threads = os.cpu_count() or 1
-  time_oracle(256, threads)                      # warm-up (thread pools, MKL)
-  t = time_oracle(512, threads)
-  rate = 512 / t                                 # rays/s
-  n = int(min(16384, max(512, rate * budget_s)) // 256 * 256)
+  threads, rate = best_thread_count()
+  n = int(min(16384, max(256, rate * budget_s)) // 256 * 256)
   t = time_oracle(n, threads)
   return {'value': n * EVALS_PER_RAY / t, 'unit': 'ray-samples/s',
           'cores': threads, 'kind': 'port',
           'sample': f'{n} rays x ({NC}+{NF}) samples, quarterhd dims, '
-                    f'torch-CPU fp32 oracle, {t:.1f} s'}
+                    f'torch-CPU fp32 oracle, {t:.1f} s; {threads} of '
+                    f'{os.cpu_count()} host threads (fastest of a probe)'}
 
 
 def run_reference(args):
@@ -176,10 +189,8 @@ def run_reference(args):
   rank = int(os.environ.get('RANK', '0'))
   if rank != 0:
     return
-  threads = os.cpu_count() or 1
-  time_oracle(256, threads)
-  t = time_oracle(512, threads)
-  n = int(min(8192, max(256, 512 / t * 8.0)) // 256 * 256)   # ~8 s per step
+  threads, rate = best_thread_count()
+  n = int(min(8192, max(256, rate * 8.0)) // 256 * 256)   # ~8 s per step
   for _ in range(min(args.warmup, 1)):
     time_oracle(n, threads)
   times = [time_oracle(n, threads) for _ in range(args.steps)]

@@ -451,6 +451,8 @@ int nfb_create(const nfb_config* cfg, int max_rays, nfb_handle** out) {
   if (cfg->num_coarse_samples < 2) return fail("num_coarse_samples must be >= 2");
   if (cfg->num_fine_samples < 0) return fail("num_fine_samples must be >= 0");
   if (cfg->precision < NFB_PREC_FP32 || cfg->precision > NFB_PREC_BF16X3) return fail("bad precision");
+  if (cfg->precision == NFB_PREC_BF16X3)
+    return fail("precision bf16x3 (fp32 emulated by 3 bf16 MMAs) is reserved and not implemented in this build");
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
     return fail("no CUDA device: nerfies_b200 has no CPU path");

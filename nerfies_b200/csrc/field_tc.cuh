@@ -263,89 +263,65 @@ field_tc_kernel(const __grid_constant__ TcProgram prog, const FieldArgs args,
     }
   } else if (warp == 8) {
     // ===================== MMA issuer =====================
-    // Warp-uniform outer control flow; inside a chunk one elected lane issues all
-    // tcgen05.mma / commits and probes the next weight unit's barrier while the
-    // current unit's last MMAs are still being queued (the tensor queue is
-    // shallow: any gap between bursts idles the pipe).
-    {
-      Tracer tr(args, lane == 0 ? 0 : -1);
-      uint32_t it = 0, xr = 0;
-      int prev_split = 99;   // first activation block produced by chunk 1 of the previous step
+    // One elected lane runs the whole flattened schedule (TcUnit table): per unit
+    // 8 tcgen05.mma + commits; the next unit's table entry is prefetched and its
+    // barriers are probed while the current unit's last MMAs are being queued, so
+    // the (shallow) tensor queue never drains at segment/chunk/step boundaries.
+    if (elect_one()) {
+      Tracer tr(args, 0);
       const uint64_t desc_hi = make_smem_desc(0);             // layout/SBO/version bits
       const uint32_t x_lo = (smem_u32(xbuf) & 0x3FFFFu) >> 4;
-      const uint32_t in_lo = (smem_u32(inbuf) & 0x3FFFFu) >> 4;
       const uint32_t st_lo = (smem_u32(stages) & 0x3FFFFu) >> 4;
+      const int u_begin = prog.unit_begin[first_step], u_end = prog.unit_begin[last_step + 1];
+      uint32_t it = 0, xr = 0;
+      const uint4* utab = reinterpret_cast<const uint4*>(prog.units);
       for (int pair = blockIdx.x; pair < num_pairs; pair += gridDim.x) {
-        for (int si = first_step; si <= last_step; ++si) {
-          const TcStep& st = prog.steps[si];
-          // step fields -> registers (constant-bank loads off the issue path)
-          const int nkb = st.nkb, nch = st.n_chunks, chunk_n = st.chunk_n, kb_free = st.kb_free;
-          uint32_t srcs = 0;
-          for (int kb = 0; kb < nkb; ++kb) srcs |= (uint32_t)st.src[kb] << (4 * kb);
-          // first K-block that reads an activation block written by chunk 1 of the
-          // previous step (needs x_ready[1]); sources are [IN?, 0, 1, 2, 3].
-          int kb_need = nkb;
-          for (int kb = nkb - 1; kb >= 0; --kb) {
-            const int b = (srcs >> (4 * kb)) & 15;
-            if (b < kSrcIn && b >= prev_split) kb_need = kb;
+        uint4 cur = utab[u_begin];
+        bool w_ready = false, x0_ready = false, x1_ready = false;
+        for (int u = u_begin; u < u_end; ++u, ++it) {
+          const uint4 nxt = utab[(u + 1 < u_end) ? u + 1 : u_begin];   // wraps to the next pair
+          const uint32_t a0 = cur.x & 0xffffu, a1 = cur.x >> 16;
+          const uint32_t dcol = cur.y & 0xffffu, chunk_n = cur.y >> 16;
+          const uint32_t flags = cur.z & 0xffffu;
+          const uint32_t nflags = nxt.z & 0xffffu;
+          const int sg = it % kStages;
+          if (flags & kUWaitX0) {
+            if (!x0_ready) mbar_wait(&bars->x_ready[0], xr & 1);
+            tr.ev(cur.z >> 16, 0);
           }
-          const uint32_t idesc = make_idesc_bf16(kTileRows, chunk_n);
-          mbar_wait(&bars->x_ready[0], xr & 1);
+          if ((flags & kUWaitX1) && !x1_ready) mbar_wait(&bars->x_ready[1], xr & 1);
+          if (!w_ready) mbar_wait(&bars->full[sg], (it / kStages) & 1);
           tc_fence_after();
-          tr.ev(si, 0);
-          bool have1 = false;
-          for (int c = 0; c < nch; ++c) {
-            if (c == 1 && !have1) { mbar_wait(&bars->x_ready[1], xr & 1); tc_fence_after(); have1 = true; }
-            for (int seg = 0; seg < 2; ++seg) {
-              const int kb0 = seg == 0 ? 0 : (have1 ? nkb : kb_need);
-              const int kb1 = seg == 0 ? (have1 ? nkb : kb_need) : nkb;
-              if (seg == 1 && kb0 < kb1) { mbar_wait(&bars->x_ready[1], xr & 1); tc_fence_after(); have1 = true; }
-              if (kb0 >= kb1) continue;
-              const uint32_t it0 = it;
-              it += (uint32_t)(kb1 - kb0);        // every lane keeps the unit counter
-              if (elect_one()) {
-                uint32_t it = it0;
-                bool ready = mbar_test(&bars->full[it % kStages], (it / kStages) & 1);
-                for (int kb = kb0; kb < kb1; ++kb, ++it) {
-                  const int sg = it % kStages;
-                  if (!ready) mbar_wait(&bars->full[sg], (it / kStages) & 1);
-                  tc_fence_after();
-                  const int b = (srcs >> (4 * kb)) & 15;
-                  const uint64_t bd = desc_hi | (uint64_t)(st_lo + sg * (kStageBytes >> 4));
-                  const uint32_t a0 = (b < kSrcIn) ? x_lo + b * (kABlockBytes >> 4) : in_lo;
-                  const uint32_t a1 = (b < kSrcIn) ? a0 + 4 * (kABlockBytes >> 4) : in_lo + (kABlockBytes >> 4);
-                  const uint64_t ad0 = desc_hi | (uint64_t)a0, ad1 = desc_hi | (uint64_t)a1;
-                  const uint32_t d0 = tmem_base + c * chunk_n, d1 = d0 + 256;
-                  umma_bf16(d0, ad0, bd, idesc, kb ? 1u : 0u);
-                  umma_bf16(d0, ad0 + 2, bd + 2, idesc, 1u);
-                  umma_bf16(d0, ad0 + 4, bd + 4, idesc, 1u);
-                  umma_bf16(d0, ad0 + 6, bd + 6, idesc, 1u);
-                  umma_bf16(d1, ad1, bd, idesc, kb ? 1u : 0u);
-                  umma_bf16(d1, ad1 + 2, bd + 2, idesc, 1u);
-                  // look ahead while the last MMAs of this unit are queued
-                  ready = (kb + 1 < kb1) && mbar_test(&bars->full[(it + 1) % kStages], ((it + 1) / kStages) & 1);
-                  umma_bf16(d1, ad1 + 4, bd + 4, idesc, 1u);
-                  umma_bf16(d1, ad1 + 6, bd + 6, idesc, 1u);
-                  umma_commit(&bars->empty[sg]);
-                  if (c == 1 && kb == kb_free) umma_commit(&bars->x_free);
-                }
-              }
-              __syncwarp();
-            }
-            if (c == nch - 1 && !have1) { mbar_wait(&bars->x_ready[1], xr & 1); tc_fence_after(); have1 = true; }
-            if (elect_one()) {
-              umma_commit(&bars->acc_ready[c]);
-              if (c == 0 && nch == 2 && kb_free < 0) umma_commit(&bars->x_free);
-            }
-            __syncwarp();
-            tr.ev(si, 1 + c);
+          const uint32_t idesc = make_idesc_bf16(kTileRows, (int)chunk_n);
+          const uint64_t bd = desc_hi | (uint64_t)(st_lo + sg * (kStageBytes >> 4));
+          const uint64_t ad0 = desc_hi | (uint64_t)(x_lo + a0), ad1 = desc_hi | (uint64_t)(x_lo + a1);
+          const uint32_t d0 = tmem_base + dcol, d1 = d0 + 256;
+          umma_bf16(d0, ad0, bd, idesc, (flags & kUAccum) ? 1u : 0u);
+          umma_bf16(d0, ad0 + 2, bd + 2, idesc, 1u);
+          umma_bf16(d0, ad0 + 4, bd + 4, idesc, 1u);
+          umma_bf16(d0, ad0 + 6, bd + 6, idesc, 1u);
+          umma_bf16(d1, ad1, bd, idesc, (flags & kUAccum) ? 1u : 0u);
+          umma_bf16(d1, ad1 + 2, bd + 2, idesc, 1u);
+          // look ahead: barriers of the next unit (phase of x_ready advances at a step end)
+          {
+            const uint32_t nxr = (flags & kUStepEnd) ? xr + 1 : xr;
+            w_ready = mbar_test(&bars->full[(it + 1) % kStages], ((it + 1) / kStages) & 1);
+            x0_ready = (nflags & kUWaitX0) && mbar_test(&bars->x_ready[0], nxr & 1);
+            x1_ready = (nflags & kUWaitX1) && mbar_test(&bars->x_ready[1], nxr & 1);
           }
-          ++xr;
-          prev_split = (nch == 2) ? chunk_n / kBlockK : 99;
+          umma_bf16(d1, ad1 + 4, bd + 4, idesc, 1u);
+          umma_bf16(d1, ad1 + 6, bd + 6, idesc, 1u);
+          umma_commit(&bars->empty[sg]);
+          if (flags & kUCommitXFree) umma_commit(&bars->x_free);
+          if (flags & kUCommitAcc0) { umma_commit(&bars->acc_ready[0]); tr.ev(cur.z >> 16, 1); }
+          if (flags & kUCommitAcc1) { umma_commit(&bars->acc_ready[1]); tr.ev(cur.z >> 16, 2); }
+          if (flags & kUStepEnd) ++xr;
+          cur = nxt;
         }
       }
-      if (lane == 0) tr.finish(args, 0);
+      tr.finish(args, 0);
     }
+    __syncwarp();
   } else {
     // ===================== epilogue: one thread per row =====================
     const int s = warp >> 2;                           // sub-tile
@@ -649,6 +625,46 @@ inline int build_tc_program(nfb_handle* h, int level, long long* wbytes, long lo
     }
   }
   if (!seen_alpha || !seen_bottleneck) return tc_fail("model without bottleneck/alpha head");
+  // Flatten the issuer's schedule (see TcUnit).
+  tp.n_units = 0;
+  int prev_split = 99;
+  for (int si = 0; si < tp.n_steps; ++si) {
+    const TcStep& t = tp.steps[si];
+    tp.unit_begin[si] = tp.n_units;
+    // A step that can start a tile pair (step 0, or the first NeRF step when the
+    // warp is skipped) follows a 1-chunk step or the prologue: nothing to split.
+    const bool after_heads = si > 0 && tp.steps[si - 1].epi != kEpiHidden;
+    if (si == 0 || after_heads) prev_split = 99;
+    int kb_need = t.nkb;
+    for (int kb = t.nkb - 1; kb >= 0; --kb)
+      if (t.src[kb] < kSrcIn && t.src[kb] >= prev_split) kb_need = kb;
+    bool have1 = false;
+    const int first = tp.n_units;
+    for (int c = 0; c < t.n_chunks; ++c)
+      for (int kb = 0; kb < t.nkb; ++kb) {
+        if (tp.n_units >= kMaxTcUnits) return tc_fail("too many weight units");
+        TcUnit& u = tp.units[tp.n_units++];
+        memset(&u, 0, sizeof(u));
+        const int b = t.src[kb];
+        const int a0 = (b < kSrcIn) ? b * kABlockBytes : kXBytes;
+        const int a1 = (b < kSrcIn) ? (4 + b) * kABlockBytes : kXBytes + kABlockBytes;
+        u.a0 = (uint16_t)(a0 >> 4); u.a1 = (uint16_t)(a1 >> 4);
+        u.dcol = (uint16_t)(c * t.chunk_n); u.chunk_n = (uint16_t)t.chunk_n; u.step = (uint16_t)si;
+        if (kb) u.flags |= kUAccum;
+        if (!have1 && (c == 1 || kb >= kb_need)) { u.flags |= kUWaitX1; have1 = true; }
+        if (kb == t.nkb - 1) u.flags |= (c == 0 ? kUCommitAcc0 : kUCommitAcc1);
+        if (t.n_chunks == 2) {
+          if (c == 1 && kb == t.kb_free) u.flags |= kUCommitXFree;
+          if (c == 0 && kb == t.nkb - 1 && t.kb_free < 0) u.flags |= kUCommitXFree;
+        }
+      }
+    tp.units[first].flags |= kUWaitX0;
+    TcUnit& last = tp.units[tp.n_units - 1];
+    if (!have1) last.flags |= kUWaitX1;   // consumed before the final commit re-arms the epilogue
+    last.flags |= kUStepEnd;
+    prev_split = (t.n_chunks == 2) ? t.chunk_n / kBlockK : 99;
+  }
+  tp.unit_begin[tp.n_steps] = tp.n_units;
   return 0;
 }
 

@@ -25,9 +25,32 @@ struct TcStep {
   int kb_free;         // chunk 1 commits "chunk-0 destination blocks are free" after this kb
 };
 
+// The MMA issuer's schedule, flattened: one entry per weight unit (8 MMAs).
+constexpr int kMaxTcUnits = 128;
+enum UnitFlags {
+  kUAccum = 1,          // first MMA accumulates (not the first K-block of the chunk)
+  kUWaitX0 = 2,         // wait x_ready[0] (first unit of a step)
+  kUWaitX1 = 4,         // wait x_ready[1] before this unit
+  kUCommitAcc0 = 8,     // commit acc_ready[0] after this unit
+  kUCommitAcc1 = 16,    // commit acc_ready[1] after this unit
+  kUCommitXFree = 32,   // commit x_free after this unit
+  kUStepEnd = 64,       // last unit of its step
+};
+struct TcUnit {
+  uint16_t a0, a1;      // A operand of sub-tile 0/1: (byte offset from the activation base) >> 4
+  uint16_t dcol;        // accumulator column offset inside the sub-tile's 256 columns
+  uint16_t chunk_n;     // MMA N
+  uint16_t flags;
+  uint16_t step;
+  uint32_t pad;
+};
+
 struct TcProgram {
   int n_steps;
   TcStep steps[kMaxTcSteps];
+  int n_units;
+  int unit_begin[kMaxTcSteps + 1];    // first unit of every step
+  TcUnit units[kMaxTcUnits];
   int warp_type, Fw, G, Fp, rc, cond_stride, sigma_act;
   int alpha_w_off, alpha_b_off;   // aux float offsets
   uint32_t units_per_pair;        // weight units streamed per tile pair

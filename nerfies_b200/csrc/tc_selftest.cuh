@@ -193,6 +193,83 @@ tc_microbench_kernel(int mode, int n, int reps, int nwarps, long long* out, cons
       if (tid == 256) { out[0] = t2 - t0; out[1] = 8LL * reps; out[2] = t1 - t0; }
       stop_flag = 1;
     }
+  } else if (mode == 3) {
+    // The current issuer: one elected-lane region per 4 units, barrier probed
+    // between the 6th and 7th MMA of a unit.  Variant bits as in mode 2 (b4 bulk
+    // copies, b5 tcgen05.ld from 8 warps) plus b2: smem st/ld traffic from warps 0-7.
+    if (warp == 9 && (nwarps & 16)) {
+      uint8_t* scratch = raw + 6 * 16384;
+      uint32_t ph = 0;
+      while (!stop_flag) {
+        if (elect_one()) { mbar_arrive_expect_tx(&bar4, 16384); bulk_g2s(scratch, gsrc, 16384, &bar4); }
+        __syncwarp();
+        mbar_wait(&bar4, ph);
+        ph ^= 1;
+      }
+    }
+    if (warp < 8 && (nwarps & (32 | 4))) {
+      const uint32_t t_lane = tmem_base + (((uint32_t)(warp & 3) * 32) << 16) + (warp >> 2) * 256;
+      uint8_t* scratch = raw + 5 * 16384;
+      float acc = 0.f;
+      while (!stop_flag) {
+        if (nwarps & 32) {
+          float va[32], vb[32];
+          tmem_ld32(t_lane + 128, va);
+          tmem_ld32(t_lane + 160, vb);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) acc += va[j] + vb[j];
+        }
+        if (nwarps & 4) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            *reinterpret_cast<uint4*>(scratch + swz_off(tid & 127, q)) = make_uint4(tid, q, 0, 0);
+            acc += *reinterpret_cast<volatile float*>(scratch + q * 16);
+          }
+        }
+        if (nwarps & 8) {     // the epilogue's hand-over: proxy fence + mbarrier arrive
+          fence_proxy_async();
+          tc_fence_before();
+          mbar_arrive(&bar2);
+        }
+      }
+      if (acc == 123.456f) out[3] = 1;
+    }
+    if (warp == 8) {
+      const uint32_t idesc = make_idesc_bf16(128, n);
+      const uint64_t hi = make_smem_desc(0);
+      const uint32_t a_lo = (smem_u32(a_blk) & 0x3FFFFu) >> 4, b_lo = (smem_u32(b_blk) & 0x3FFFFu) >> 4;
+      const long long t0 = clock64();
+      for (int r = 0; r < reps; r += 4) {
+        if (elect_one()) {
+          bool ready = mbar_test(&bar3, 1);
+          for (int u = 0; u < 4; ++u) {
+            if (!ready) mbar_wait(&bar3, 1);
+            tc_fence_after();
+            const uint64_t bd = hi | (uint64_t)(b_lo + (u & 3) * 1024);
+            const uint64_t ad0 = hi | (uint64_t)a_lo, ad1 = hi | (uint64_t)(a_lo + 512);
+            umma_bf16(tmem_base, ad0, bd, idesc, 1u);
+            umma_bf16(tmem_base, ad0 + 2, bd + 2, idesc, 1u);
+            umma_bf16(tmem_base, ad0 + 4, bd + 4, idesc, 1u);
+            umma_bf16(tmem_base, ad0 + 6, bd + 6, idesc, 1u);
+            umma_bf16(tmem_base + 256, ad1, bd, idesc, 1u);
+            umma_bf16(tmem_base + 256, ad1 + 2, bd + 2, idesc, 1u);
+            ready = mbar_test(&bar3, 1);
+            umma_bf16(tmem_base + 256, ad1 + 4, bd + 4, idesc, 1u);
+            umma_bf16(tmem_base + 256, ad1 + 6, bd + 6, idesc, 1u);
+            umma_commit(&bar2);
+          }
+        }
+        __syncwarp();
+      }
+      if (elect_one()) umma_commit(&bar);
+      __syncwarp();
+      const long long t1 = clock64();
+      mbar_wait(&bar, 0);
+      const long long t2 = clock64();
+      if (tid == 256) { out[0] = t2 - t0; out[1] = 8LL * reps; out[2] = t1 - t0; }
+      stop_flag = 1;
+    }
   } else if (mode == 0) {
     if (tid == 256) {
       const uint32_t idesc = make_idesc_bf16(128, n);

@@ -15,6 +15,9 @@ for variant in (1, 2, 3, 4, 7):
 for variant in (4, 12, 20, 36, 60):
   _lib.check(lib.nfb_selftest_microbench(2, 128, 512, variant, out))
   print(f'issue-loop N=128 variant {variant:06b} (b2 commit/unit, b3 B cycles 4 stages, b4 concurrent bulk copies, b5 concurrent LDTM x8 warps): {out[0]/out[1]:.1f} cycles/MMA')
+for variant in (0, 52, 8, 12, 60):
+  _lib.check(lib.nfb_selftest_microbench(3, 128, 512, variant, out))
+  print(f'probe-ahead issuer N=128 variant {variant:06b} (b2 smem st/ld x8 warps, b3 fence.proxy.async+arrive, b4 bulk copies, b5 LDTM x8 warps): {out[0]/out[1]:.1f} cycles/MMA')
 for nw in (1, 4, 8):
   _lib.check(lib.nfb_selftest_microbench(1, 128, 256, nw, out))
   per = out[0] / out[1]

@@ -30,7 +30,10 @@ recs = []
 for role in range(4):
   for i in range(min(t[role], per)):
     tag, clk = t[4 + role * per * 2 + 2 * i], t[4 + role * per * 2 + 2 * i + 1]
-    recs.append((role, tag >> 8, tag & 0xff, clk))
+    if role == 0 and (tag & 0xff) == 40:
+      recs.append((role, tag >> 8, 40, recs[-1][3] + 1, clk))
+    else:
+      recs.append((role, tag >> 8, tag & 0xff, clk, 0))
 n = len(recs)
 t0 = min(r[3] for r in recs)
 recs.sort(key=lambda r: r[3])
@@ -47,7 +50,11 @@ if len(starts) > 2:
   lo, hi = int(os.environ.get('STEP_LO', '8')), int(os.environ.get('STEP_HI', '10'))
   for r in recs[a:b]:
     if lo <= r[1] <= hi:
-      if r[0] == 3: nm = 'PROD copy issued unit %d' % r[2]
+      if r[0] == 0 and r[2] == 40:
+        print('          step %2d  MMA  weight waits in segment: %d cycles, %d misses' % (r[1], r[4] >> 8, r[4] & 0xff)); continue
+      if r[0] == 0 and 20 <= r[2] < 30: nm = 'MMA  segment begin c%d seg%d' % ((r[2] - 20) // 2, (r[2] - 20) % 2)
+      elif r[0] == 0 and 30 <= r[2] < 40: nm = 'MMA  segment issued c%d seg%d' % ((r[2] - 30) // 2, (r[2] - 30) % 2)
+      elif r[0] == 3: nm = 'PROD copy issued unit %d' % r[2]
       elif r[0] == 0 and r[2] >= 30: nm = 'MMA  got weights c%d kb%d' % ((r[2] - 30) // 8, (r[2] - 30) % 8)
       elif r[0] == 0 and r[2] >= 10: nm = 'MMA  wait weights c%d kb%d' % ((r[2] - 10) // 8, (r[2] - 10) % 8)
       else: nm = names[r[0]][r[2]]

@@ -46,6 +46,7 @@ struct FieldArgs {
   int use_warp;              // run the warp net
   int warp_only;             // stop after the warp (nfb_warp_forward)
   int fast_encode;           // bf16 mode: octave-recurrence positional encoding
+  int debug;                 // NFB_DEBUG bits: 1 = epilogue skips TMEM loads/math/stores (timing experiments)
   long long* trace;          // debug: (tag, clock) records of block 0, or nullptr
   int trace_cap;
 };

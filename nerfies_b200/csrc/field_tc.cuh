@@ -263,65 +263,63 @@ field_tc_kernel(const __grid_constant__ TcProgram prog, const FieldArgs args,
     }
   } else if (warp == 8) {
     // ===================== MMA issuer =====================
-    // One elected lane runs the whole flattened schedule (TcUnit table): per unit
-    // 8 tcgen05.mma + commits; the next unit's table entry is prefetched and its
-    // barriers are probed while the current unit's last MMAs are being queued, so
-    // the (shallow) tensor queue never drains at segment/chunk/step boundaries.
-    if (elect_one()) {
-      Tracer tr(args, 0);
+    // The whole warp walks the flattened schedule (TcUnit table) in uniform
+    // control flow - table decode, barrier waits and look-ahead probes stay in
+    // uniform registers - and one elected lane issues each unit's 8 tcgen05.mma
+    // plus its commits.  No nested step/chunk/segment loops: the (shallow)
+    // tensor queue must not drain at boundaries.
+    {
+      Tracer tr(args, lane == 0 ? 0 : -1);
       const uint64_t desc_hi = make_smem_desc(0);             // layout/SBO/version bits
       const uint32_t x_lo = (smem_u32(xbuf) & 0x3FFFFu) >> 4;
       const uint32_t st_lo = (smem_u32(stages) & 0x3FFFFu) >> 4;
       const int u_begin = prog.unit_begin[first_step], u_end = prog.unit_begin[last_step + 1];
-      uint32_t it = 0, xr = 0;
-      const uint4* utab = reinterpret_cast<const uint4*>(prog.units);
+      uint32_t sg = 0, wph = 0, xr = 0;     // weight stage / its phase parity / x_ready phase
       for (int pair = blockIdx.x; pair < num_pairs; pair += gridDim.x) {
-        uint4 cur = utab[u_begin];
         bool w_ready = false, x0_ready = false, x1_ready = false;
-        for (int u = u_begin; u < u_end; ++u, ++it) {
-          const uint4 nxt = utab[(u + 1 < u_end) ? u + 1 : u_begin];   // wraps to the next pair
-          const uint32_t a0 = cur.x & 0xffffu, a1 = cur.x >> 16;
-          const uint32_t dcol = cur.y & 0xffffu, chunk_n = cur.y >> 16;
-          const uint32_t flags = cur.z & 0xffffu;
-          const uint32_t nflags = nxt.z & 0xffffu;
-          const int sg = it % kStages;
+        for (int u = u_begin; u < u_end; ++u) {
+          const TcUnit un = prog.units[u];
+          const uint32_t flags = un.flags;
           if (flags & kUWaitX0) {
             if (!x0_ready) mbar_wait(&bars->x_ready[0], xr & 1);
-            tr.ev(cur.z >> 16, 0);
+            tr.ev(un.step, 0);
           }
           if ((flags & kUWaitX1) && !x1_ready) mbar_wait(&bars->x_ready[1], xr & 1);
-          if (!w_ready) mbar_wait(&bars->full[sg], (it / kStages) & 1);
+          if (!w_ready) mbar_wait(&bars->full[sg], wph);
           tc_fence_after();
-          const uint32_t idesc = make_idesc_bf16(kTileRows, (int)chunk_n);
-          const uint64_t bd = desc_hi | (uint64_t)(st_lo + sg * (kStageBytes >> 4));
-          const uint64_t ad0 = desc_hi | (uint64_t)(x_lo + a0), ad1 = desc_hi | (uint64_t)(x_lo + a1);
-          const uint32_t d0 = tmem_base + dcol, d1 = d0 + 256;
-          umma_bf16(d0, ad0, bd, idesc, (flags & kUAccum) ? 1u : 0u);
-          umma_bf16(d0, ad0 + 2, bd + 2, idesc, 1u);
-          umma_bf16(d0, ad0 + 4, bd + 4, idesc, 1u);
-          umma_bf16(d0, ad0 + 6, bd + 6, idesc, 1u);
-          umma_bf16(d1, ad1, bd, idesc, (flags & kUAccum) ? 1u : 0u);
-          umma_bf16(d1, ad1 + 2, bd + 2, idesc, 1u);
-          // look ahead: barriers of the next unit (phase of x_ready advances at a step end)
-          {
-            const uint32_t nxr = (flags & kUStepEnd) ? xr + 1 : xr;
-            w_ready = mbar_test(&bars->full[(it + 1) % kStages], ((it + 1) / kStages) & 1);
-            x0_ready = (nflags & kUWaitX0) && mbar_test(&bars->x_ready[0], nxr & 1);
-            x1_ready = (nflags & kUWaitX1) && mbar_test(&bars->x_ready[1], nxr & 1);
+          if (elect_one()) {
+            const uint32_t idesc = make_idesc_bf16(kTileRows, (int)un.chunk_n);
+            const uint64_t bd = desc_hi | (uint64_t)(st_lo + sg * (kStageBytes >> 4));
+            const uint64_t ad0 = desc_hi | (uint64_t)(x_lo + un.a0), ad1 = desc_hi | (uint64_t)(x_lo + un.a1);
+            const uint32_t d0 = tmem_base + un.dcol, d1 = d0 + 256;
+            const uint32_t acc = (flags & kUAccum) ? 1u : 0u;
+            umma_bf16(d0, ad0, bd, idesc, acc);
+            umma_bf16(d0, ad0 + 2, bd + 2, idesc, 1u);
+            umma_bf16(d0, ad0 + 4, bd + 4, idesc, 1u);
+            umma_bf16(d0, ad0 + 6, bd + 6, idesc, 1u);
+            umma_bf16(d1, ad1, bd, idesc, acc);
+            umma_bf16(d1, ad1 + 2, bd + 2, idesc, 1u);
+            umma_bf16(d1, ad1 + 4, bd + 4, idesc, 1u);
+            umma_bf16(d1, ad1 + 6, bd + 6, idesc, 1u);
+            umma_commit(&bars->empty[sg]);
+            if (flags & kUCommitXFree) umma_commit(&bars->x_free);
+            if (flags & kUCommitAcc0) umma_commit(&bars->acc_ready[0]);
+            if (flags & kUCommitAcc1) umma_commit(&bars->acc_ready[1]);
           }
-          umma_bf16(d1, ad1 + 4, bd + 4, idesc, 1u);
-          umma_bf16(d1, ad1 + 6, bd + 6, idesc, 1u);
-          umma_commit(&bars->empty[sg]);
-          if (flags & kUCommitXFree) umma_commit(&bars->x_free);
-          if (flags & kUCommitAcc0) { umma_commit(&bars->acc_ready[0]); tr.ev(cur.z >> 16, 1); }
-          if (flags & kUCommitAcc1) { umma_commit(&bars->acc_ready[1]); tr.ev(cur.z >> 16, 2); }
+          __syncwarp();
+          if (flags & (kUCommitAcc0 | kUCommitAcc1)) tr.ev(un.step, (flags & kUCommitAcc0) ? 1 : 2);
+          // advance, then look ahead at the next unit's barriers while the MMAs just
+          // issued are still executing
           if (flags & kUStepEnd) ++xr;
-          cur = nxt;
+          if (++sg == kStages) { sg = 0; wph ^= 1; }
+          const uint32_t nflags = prog.units[(u + 1 < u_end) ? u + 1 : u_begin].flags;
+          w_ready = mbar_test(&bars->full[sg], wph);
+          x0_ready = (nflags & kUWaitX0) ? mbar_test(&bars->x_ready[0], xr & 1) : false;
+          x1_ready = (nflags & kUWaitX1) ? mbar_test(&bars->x_ready[1], xr & 1) : false;
         }
       }
-      tr.finish(args, 0);
+      if (lane == 0) tr.finish(args, 0);
     }
-    __syncwarp();
   } else {
     // ===================== epilogue: one thread per row =====================
     const int s = warp >> 2;                           // sub-tile
@@ -399,7 +397,7 @@ field_tc_kernel(const __grid_constant__ TcProgram prog, const FieldArgs args,
           tr.ev(si, 0);
 #pragma unroll
           for (int pp = 0; pp < 2; ++pp) {
-            if (2 * pp < np) {
+            if (2 * pp < np && !(args.debug & 1)) {
               float va[32], vb[32];
               tmem_ld32(t_lane + (2 * pp) * 32, va);
               tmem_ld32(t_lane + (2 * pp + 1) * 32, vb);
@@ -413,7 +411,7 @@ field_tc_kernel(const __grid_constant__ TcProgram prog, const FieldArgs args,
           tr.ev(si, 2);
 #pragma unroll
           for (int p = 0; p < 4; ++p) {
-            if (p < np) {
+            if (p < np && !(args.debug & 1)) {
               uint8_t* blk = xs + (p >> 1) * kABlockBytes;
 #pragma unroll
               for (int q = 0; q < 4; ++q) {
@@ -437,7 +435,7 @@ field_tc_kernel(const __grid_constant__ TcProgram prog, const FieldArgs args,
           tr.ev(si, 4);
 #pragma unroll
           for (int pp = 0; pp < 2; ++pp) {
-            if (2 * pp < np) {
+            if (2 * pp < np && !(args.debug & 1)) {
               float va[32], vb[32];
               const int col0 = st.chunk_n + 2 * pp * 32;
               tmem_ld32(t_lane + col0, va);

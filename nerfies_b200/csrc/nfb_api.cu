@@ -6,6 +6,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <string>
 #include <vector>
 
@@ -307,6 +308,10 @@ int run_field(nfb_handle* h, int level, long long rows, int S, const float* orig
   a.num_rows = rows; a.samples_per_ray = S; a.use_warp = use_warp; a.warp_only = warp_only;
   a.fast_encode = h->cfg.precision == NFB_PREC_BF16;
   a.trace = h->trace; a.trace_cap = h->trace_cap;
+  {
+    static const int dbg = getenv("NFB_DEBUG") ? atoi(getenv("NFB_DEBUG")) : 0;
+    a.debug = dbg;
+  }
   const bool prof = h->profiling && !warp_only;
   if (prof) NFB_CUDA(cudaEventRecord(h->ev[level][0], s));
   int rc;
@@ -436,7 +441,10 @@ int nfb_selftest_microbench(int mode, int n, int reps, int nwarps, long long* ou
   NFB_CUDA(cudaMemset(g, 0, 16384));
   const int smem = 7 * 16384;
   NFB_CUDA(cudaFuncSetAttribute(tc_microbench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  tc_microbench_kernel<<<1, 320, smem>>>(mode, n, reps, nwarps, d, g);
+  // mode bits 9..: grid size minus one (chip-wide contention experiments)
+  const int grid = (mode >> 9) + 1;
+  mode &= 511;
+  tc_microbench_kernel<<<grid, 320, smem>>>(mode, n, reps, nwarps, d, g);
   cudaError_t e = cudaDeviceSynchronize();
   cudaFree(g);
   if (e == cudaSuccess) e = cudaMemcpy(out, d, 3 * sizeof(long long), cudaMemcpyDeviceToHost);

@@ -126,7 +126,17 @@ tc_microbench_kernel(int mode, int n, int reps, int nwarps, long long* out, cons
   const int tid = threadIdx.x, warp = tid >> 5;
   if (tid == 0) stop_flag = 0;
   for (int i = tid; i < 7 * 16384 / 4; i += blockDim.x)
-    reinterpret_cast<uint32_t*>(raw)[i] = 0x3c003c00u;   // small bf16 values
+  {
+    // small bf16 values: constant, or (mode bit 8) pseudo-random mantissas/signs
+    uint32_t v = 0x3c003c00u;
+    if (mode & 256) {
+      uint32_t hsh = (uint32_t)i * 2654435761u;
+      hsh ^= hsh >> 15; hsh *= 2246822519u; hsh ^= hsh >> 13;
+      v = (hsh & 0x80ff80ffu) | 0x3c003c00u;
+    }
+    reinterpret_cast<uint32_t*>(raw)[i] = v;
+  }
+  mode &= 255;
   if (tid == 256) { mbar_init(&bar, 1); mbar_init(&bar2, 1 << 20); mbar_init(&bar3, 1); mbar_init(&bar4, 1); fence_barrier_init(); }
   if (warp == 8) tmem_alloc(&tmem_slot, 512);
   fence_proxy_async();
@@ -267,7 +277,7 @@ tc_microbench_kernel(int mode, int n, int reps, int nwarps, long long* out, cons
       const long long t1 = clock64();
       mbar_wait(&bar, 0);
       const long long t2 = clock64();
-      if (tid == 256) { out[0] = t2 - t0; out[1] = 8LL * reps; out[2] = t1 - t0; }
+      if (tid == 256 && blockIdx.x == 0) { out[0] = t2 - t0; out[1] = 8LL * reps; out[2] = t1 - t0; }
       stop_flag = 1;
     }
   } else if (mode == 0) {

@@ -15,9 +15,18 @@ for variant in (1, 2, 3, 4, 7):
 for variant in (4, 12, 20, 36, 60):
   _lib.check(lib.nfb_selftest_microbench(2, 128, 512, variant, out))
   print(f'issue-loop N=128 variant {variant:06b} (b2 commit/unit, b3 B cycles 4 stages, b4 concurrent bulk copies, b5 concurrent LDTM x8 warps): {out[0]/out[1]:.1f} cycles/MMA')
-for variant in (0, 52, 8, 12, 60):
+for variant in (0, 52):
   _lib.check(lib.nfb_selftest_microbench(3, 128, 512, variant, out))
   print(f'probe-ahead issuer N=128 variant {variant:06b} (b2 smem st/ld x8 warps, b3 fence.proxy.async+arrive, b4 bulk copies, b5 LDTM x8 warps): {out[0]/out[1]:.1f} cycles/MMA')
+for mode in (3, 3 + 256):
+  _lib.check(lib.nfb_selftest_microbench(mode, 128, 512, 0, out))
+  print(f'probe-ahead issuer N=128, {"random" if mode & 256 else "constant"} operand data: {out[0]/out[1]:.1f} cycles/MMA')
+for grid in (1, 2, 8, 74, 148):
+  _lib.check(lib.nfb_selftest_microbench(3 + ((grid - 1) << 9), 128, 2048, 0, out))
+  print(f'probe-ahead issuer N=128 on {grid} CTAs/SMs concurrently: {out[0]/out[1]:.1f} cycles/MMA (block 0)')
+for mode in (0, 256):
+  _lib.check(lib.nfb_selftest_microbench(mode, 256, 512, 0, out))
+  print(f'MMA chain N=256, {"random" if mode & 256 else "constant"} operand data: {out[0]/out[1]:.1f} cycles/MMA')
 for nw in (1, 4, 8):
   _lib.check(lib.nfb_selftest_microbench(1, 128, 256, nw, out))
   per = out[0] / out[1]

@@ -213,7 +213,7 @@ def run_reference(args):
               'd2h_bytes_per_step': 0},
       'gpu_launches': 0,
   }
-  print(json.dumps(line), flush=True)
+  emit(line)
 
 
 def run_b200(args):
@@ -383,7 +383,7 @@ def run_b200(args):
   }
   if not args.no_cpu_baseline:
     line['cpu_baseline'] = cpu_baseline(args.cpu_seconds)
-  print(json.dumps(line), flush=True)
+  emit(line)
   if world > 1:
     dist.destroy_process_group()
 
@@ -394,8 +394,28 @@ def default_precision():
       REPO, 'nerfies_b200', 'csrc', 'field_tc.cuh')) else 'fp32'
 
 
+_SAVED_STDOUT = None
+
+
+def quiet_stdout():
+  """Route fd 1 to stderr until emit(): libraries (NCCL's version banner, ...)
+  must not print in front of the one JSON line the driver parses."""
+  global _SAVED_STDOUT
+  sys.stdout.flush()
+  _SAVED_STDOUT = os.dup(1)
+  os.dup2(2, 1)
+
+
+def emit(line):
+  sys.stdout.flush()
+  if _SAVED_STDOUT is not None:
+    os.dup2(_SAVED_STDOUT, 1)
+  print(json.dumps(line), flush=True)
+
+
 def main():
   args = parse_args()
+  quiet_stdout()
   if args.impl == 'reference':
     run_reference(args)
   else:

@@ -263,63 +263,54 @@ field_tc_kernel(const __grid_constant__ TcProgram prog, const FieldArgs args,
     }
   } else if (warp == 8) {
     // ===================== MMA issuer =====================
-    // The whole warp walks the flattened schedule (TcUnit table) in uniform
-    // control flow - table decode, barrier waits and look-ahead probes stay in
-    // uniform registers - and one elected lane issues each unit's 8 tcgen05.mma
-    // plus its commits.  No nested step/chunk/segment loops: the (shallow)
-    // tensor queue must not drain at boundaries.
-    {
-      Tracer tr(args, lane == 0 ? 0 : -1);
+    // One elected lane walks the flattened schedule (TcUnit table).  Each unit is
+    // a single issue_unit() block: fence, look-ahead probes of the next unit's
+    // barriers, 8 tcgen05.mma, commits; the next table entry is prefetched.  The
+    // (shallow) tensor queue therefore never waits on barrier latency.
+    if (elect_one()) {
+      Tracer tr(args, 0);
       const uint64_t desc_hi = make_smem_desc(0);             // layout/SBO/version bits
       const uint32_t x_lo = (smem_u32(xbuf) & 0x3FFFFu) >> 4;
       const uint32_t st_lo = (smem_u32(stages) & 0x3FFFFu) >> 4;
+      const uint32_t b_full = smem_u32(&bars->full[0]), b_empty = smem_u32(&bars->empty[0]);
+      const uint32_t b_acc0 = smem_u32(&bars->acc_ready[0]), b_acc1 = smem_u32(&bars->acc_ready[1]);
+      const uint32_t b_xfree = smem_u32(&bars->x_free);
+      const uint32_t b_x0 = smem_u32(&bars->x_ready[0]), b_x1 = smem_u32(&bars->x_ready[1]);
       const int u_begin = prog.unit_begin[first_step], u_end = prog.unit_begin[last_step + 1];
-      uint32_t sg = 0, wph = 0, xr = 0;     // weight stage / its phase parity / x_ready phase
+      const uint4* utab = reinterpret_cast<const uint4*>(prog.units);
+      uint32_t sg = 0, wph = 0, xr = 0;     // weight stage, its phase parity, x_ready phase
+      uint32_t ready = 0;                    // look-ahead results for the unit about to issue
+      uint4 cur = utab[u_begin];
       for (int pair = blockIdx.x; pair < num_pairs; pair += gridDim.x) {
-        bool w_ready = false, x0_ready = false, x1_ready = false;
         for (int u = u_begin; u < u_end; ++u) {
-          const TcUnit un = prog.units[u];
-          const uint32_t flags = un.flags;
-          if (flags & kUWaitX0) {
-            if (!x0_ready) mbar_wait(&bars->x_ready[0], xr & 1);
-            tr.ev(un.step, 0);
-          }
-          if ((flags & kUWaitX1) && !x1_ready) mbar_wait(&bars->x_ready[1], xr & 1);
-          if (!w_ready) mbar_wait(&bars->full[sg], wph);
-          tc_fence_after();
-          if (elect_one()) {
-            const uint32_t idesc = make_idesc_bf16(kTileRows, (int)un.chunk_n);
-            const uint64_t bd = desc_hi | (uint64_t)(st_lo + sg * (kStageBytes >> 4));
-            const uint64_t ad0 = desc_hi | (uint64_t)(x_lo + un.a0), ad1 = desc_hi | (uint64_t)(x_lo + un.a1);
-            const uint32_t d0 = tmem_base + un.dcol, d1 = d0 + 256;
-            const uint32_t acc = (flags & kUAccum) ? 1u : 0u;
-            umma_bf16(d0, ad0, bd, idesc, acc);
-            umma_bf16(d0, ad0 + 2, bd + 2, idesc, 1u);
-            umma_bf16(d0, ad0 + 4, bd + 4, idesc, 1u);
-            umma_bf16(d0, ad0 + 6, bd + 6, idesc, 1u);
-            umma_bf16(d1, ad1, bd, idesc, acc);
-            umma_bf16(d1, ad1 + 2, bd + 2, idesc, 1u);
-            umma_bf16(d1, ad1 + 4, bd + 4, idesc, 1u);
-            umma_bf16(d1, ad1 + 6, bd + 6, idesc, 1u);
-            umma_commit(&bars->empty[sg]);
-            if (flags & kUCommitXFree) umma_commit(&bars->x_free);
-            if (flags & kUCommitAcc0) umma_commit(&bars->acc_ready[0]);
-            if (flags & kUCommitAcc1) umma_commit(&bars->acc_ready[1]);
-          }
-          __syncwarp();
-          if (flags & (kUCommitAcc0 | kUCommitAcc1)) tr.ev(un.step, (flags & kUCommitAcc0) ? 1 : 2);
-          // advance, then look ahead at the next unit's barriers while the MMAs just
-          // issued are still executing
-          if (flags & kUStepEnd) ++xr;
-          if (++sg == kStages) { sg = 0; wph ^= 1; }
-          const uint32_t nflags = prog.units[(u + 1 < u_end) ? u + 1 : u_begin].flags;
-          w_ready = mbar_test(&bars->full[sg], wph);
-          x0_ready = (nflags & kUWaitX0) ? mbar_test(&bars->x_ready[0], xr & 1) : false;
-          x1_ready = (nflags & kUWaitX1) ? mbar_test(&bars->x_ready[1], xr & 1) : false;
+          const uint4 nxt = utab[(u + 1 < u_end) ? u + 1 : u_begin];   // wraps into the next pair
+          const uint32_t flags = cur.z & 0xffffu, nflags = nxt.z & 0xffffu;
+          if ((flags & kUWaitX0) && !(ready & 2)) mbar_wait(&bars->x_ready[0], xr & 1);
+          if (flags & kUWaitX0) tr.ev(cur.z >> 16, 0);
+          if ((flags & kUWaitX1) && !(ready & 4)) mbar_wait(&bars->x_ready[1], xr & 1);
+          if (!(ready & 1)) mbar_wait(&bars->full[sg], wph);
+          const uint32_t chunk_n = cur.y >> 16;
+          const uint32_t idesc = make_idesc_bf16(kTileRows, (int)chunk_n);
+          const uint64_t bd = desc_hi | (uint64_t)(st_lo + sg * (kStageBytes >> 4));
+          const uint64_t ad0 = desc_hi | (uint64_t)(x_lo + (cur.x & 0xffffu));
+          const uint64_t ad1 = desc_hi | (uint64_t)(x_lo + (cur.x >> 16));
+          const uint32_t d0 = tmem_base + (cur.y & 0xffffu);
+          const uint32_t nsg = (sg + 1 == kStages) ? 0 : sg + 1;
+          const uint32_t nwph = (sg + 1 == kStages) ? wph ^ 1 : wph;
+          const uint32_t nxr = (flags & kUStepEnd) ? xr + 1 : xr;
+          ready = issue_unit(d0, d0 + 256, ad0, ad1, bd, idesc, (flags & kUAccum) ? 1u : 0u,
+                             b_empty + sg * 8, (flags & kUCommitXFree) ? b_xfree : 0u,
+                             (flags & kUCommitAcc0) ? b_acc0 : ((flags & kUCommitAcc1) ? b_acc1 : 0u),
+                             b_full + nsg * 8, nwph, (nflags & kUWaitX0) ? b_x0 : 0u,
+                             (nflags & kUWaitX1) ? b_x1 : 0u, nxr & 1);
+          if (flags & (kUCommitAcc0 | kUCommitAcc1)) tr.ev(cur.z >> 16, (flags & kUCommitAcc0) ? 1 : 2);
+          sg = nsg; wph = nwph; xr = nxr;
+          cur = nxt;
         }
       }
-      if (lane == 0) tr.finish(args, 0);
+      tr.finish(args, 0);
     }
+    __syncwarp();
   } else {
     // ===================== epilogue: one thread per row =====================
     const int s = warp >> 2;                           // sub-tile

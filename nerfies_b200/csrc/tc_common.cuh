@@ -193,6 +193,65 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
                : "memory");
 }
 
+// One weight unit of the fused field kernel, issued by a single thread as ONE
+// instruction block: tcgen05.fence, non-blocking probes of the barriers the NEXT
+// unit will need, 8 tcgen05.mma (4 K-slices x 2 sub-tiles), the commits - and
+// only then the probe results are read.  mbarrier probes cost 90-150 cycles and
+// the tensor queue is shallow, so a probe *between* units would idle the pipe;
+// here it is in flight while the MMAs queue.
+//   bar_* are shared-memory addresses (0 = skip); returns bit0/1/2 = the probed
+//   weight / x_ready[0] / x_ready[1] phase is complete.
+__device__ __forceinline__ uint32_t issue_unit(uint32_t d0, uint32_t d1, uint64_t ad0, uint64_t ad1,
+                                               uint64_t bd, uint32_t idesc, uint32_t accumulate,
+                                               uint32_t bar_empty, uint32_t bar_xfree,
+                                               uint32_t bar_acc, uint32_t probe_w, uint32_t par_w,
+                                               uint32_t probe_x0, uint32_t probe_x1, uint32_t par_x) {
+  uint32_t out;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred pacc, pt, pw, px0, px1, pd0, pd1, pcx, pca;\n\t"
+      ".reg .b64 a01, a02, a03, a11, a12, a13, b1, b2, b3;\n\t"
+      ".reg .b32 t0, t1;\n\t"
+      "tcgen05.fence::after_thread_sync;\n\t"
+      "setp.ne.b32 pacc, %7, 0;\n\t"
+      "setp.eq.b32 pt, 0, 0;\n\t"
+      "setp.ne.b32 pd0, %13, 0;\n\t"
+      "setp.ne.b32 pd1, %14, 0;\n\t"
+      "setp.ne.b32 pcx, %9, 0;\n\t"
+      "setp.ne.b32 pca, %10, 0;\n\t"
+      "setp.eq.b32 px0, 1, 0;\n\t"
+      "setp.eq.b32 px1, 1, 0;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 pw, [%11], %12;\n\t"
+      "@pd0 mbarrier.test_wait.parity.shared::cta.b64 px0, [%13], %15;\n\t"
+      "@pd1 mbarrier.test_wait.parity.shared::cta.b64 px1, [%14], %15;\n\t"
+      "add.u64 a01, %3, 2;\n\t add.u64 a02, %3, 4;\n\t add.u64 a03, %3, 6;\n\t"
+      "add.u64 a11, %4, 2;\n\t add.u64 a12, %4, 4;\n\t add.u64 a13, %4, 6;\n\t"
+      "add.u64 b1, %5, 2;\n\t add.u64 b2, %5, 4;\n\t add.u64 b3, %5, 6;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%1], %3, %5, %6, pacc;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%1], a01, b1, %6, pt;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%1], a02, b2, %6, pt;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%1], a03, b3, %6, pt;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%2], %4, %5, %6, pacc;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%2], a11, b1, %6, pt;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%2], a12, b2, %6, pt;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%2], a13, b3, %6, pt;\n\t"
+      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%8];\n\t"
+      "@pcx tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%9];\n\t"
+      "@pca tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%10];\n\t"
+      "selp.u32 %0, 1, 0, pw;\n\t"
+      "selp.u32 t0, 2, 0, px0;\n\t"
+      "selp.u32 t1, 4, 0, px1;\n\t"
+      "or.b32 %0, %0, t0;\n\t"
+      "or.b32 %0, %0, t1;\n\t"
+      "}"
+      : "=r"(out)
+      : "r"(d0), "r"(d1), "l"(ad0), "l"(ad1), "l"(bd), "r"(idesc), "r"(accumulate), "r"(bar_empty),
+        "r"(bar_xfree), "r"(bar_acc), "r"(probe_w), "r"(par_w), "r"(probe_x0), "r"(probe_x1),
+        "r"(par_x)
+      : "memory");
+  return out;
+}
+
 // ---- bf16 helpers ---------------------------------------------------------------
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);

@@ -263,49 +263,56 @@ field_tc_kernel(const __grid_constant__ TcProgram prog, const FieldArgs args,
     }
   } else if (warp == 8) {
     // ===================== MMA issuer =====================
-    // One elected lane walks the flattened schedule (TcUnit table).  Each unit is
-    // a single issue_unit() block: fence, look-ahead probes of the next unit's
-    // barriers, 8 tcgen05.mma, commits; the next table entry is prefetched.  The
-    // (shallow) tensor queue therefore never waits on barrier latency.
+    // One elected lane walks the flattened, host-precomputed schedule (TcUnit).
+    // Per unit: one issue_unit() block (fence, look-ahead probes of the next unit's
+    // barriers, 8 tcgen05.mma, the stage-release commit).  The code between two
+    // issue blocks is a handful of instructions: a single thread runs alone here,
+    // every dependent instruction on this path is ~5 idle cycles of the tensor pipe.
     if (elect_one()) {
       Tracer tr(args, 0);
-      const uint64_t desc_hi = make_smem_desc(0);             // layout/SBO/version bits
-      const uint32_t x_lo = (smem_u32(xbuf) & 0x3FFFFu) >> 4;
-      const uint32_t st_lo = (smem_u32(stages) & 0x3FFFFu) >> 4;
+      const uint64_t desc_hi = make_smem_desc(0) & 0xFFFFFFFF00000000ull;   // SBO/version/layout
+      const uint32_t lo_base = ((smem_u32(xbuf) & 0x3FFFFu) >> 4) | (1u << 16);   // + LBO field
+      const uint32_t st_lo = ((smem_u32(stages) & 0x3FFFFu) >> 4) | (1u << 16);
       const uint32_t b_full = smem_u32(&bars->full[0]), b_empty = smem_u32(&bars->empty[0]);
       const uint32_t b_acc0 = smem_u32(&bars->acc_ready[0]), b_acc1 = smem_u32(&bars->acc_ready[1]);
       const uint32_t b_xfree = smem_u32(&bars->x_free);
       const uint32_t b_x0 = smem_u32(&bars->x_ready[0]), b_x1 = smem_u32(&bars->x_ready[1]);
       const int u_begin = prog.unit_begin[first_step], u_end = prog.unit_begin[last_step + 1];
-      const uint4* utab = reinterpret_cast<const uint4*>(prog.units);
-      uint32_t sg = 0, wph = 0, xr = 0;     // weight stage, its phase parity, x_ready phase
-      uint32_t ready = 0;                    // look-ahead results for the unit about to issue
-      uint4 cur = utab[u_begin];
+      const int n_u = u_end - u_begin;
+      const uint4* utab = reinterpret_cast<const uint4*>(prog.units);   // 2 x uint4 per unit
+      uint32_t sg = 0, wph = 0, xr = 0, ready = 0;
+      // entries are fetched TWO units ahead (constant bank, dynamic index)
+      uint4 c0 = utab[2 * u_begin], c1 = utab[2 * u_begin + 1];
+      int un = u_begin + (1 % n_u);
+      uint4 n0 = utab[2 * un], n1 = utab[2 * un + 1];
       for (int pair = blockIdx.x; pair < num_pairs; pair += gridDim.x) {
         for (int u = u_begin; u < u_end; ++u) {
-          const uint4 nxt = utab[(u + 1 < u_end) ? u + 1 : u_begin];   // wraps into the next pair
-          const uint32_t flags = cur.z & 0xffffu, nflags = nxt.z & 0xffffu;
-          if ((flags & kUWaitX0) && !(ready & 2)) mbar_wait(&bars->x_ready[0], xr & 1);
-          if (flags & kUWaitX0) tr.ev(cur.z >> 16, 0);
-          if ((flags & kUWaitX1) && !(ready & 4)) mbar_wait(&bars->x_ready[1], xr & 1);
-          if (!(ready & 1)) mbar_wait(&bars->full[sg], wph);
-          const uint32_t chunk_n = cur.y >> 16;
-          const uint32_t idesc = make_idesc_bf16(kTileRows, (int)chunk_n);
-          const uint64_t bd = desc_hi | (uint64_t)(st_lo + sg * (kStageBytes >> 4));
-          const uint64_t ad0 = desc_hi | (uint64_t)(x_lo + (cur.x & 0xffffu));
-          const uint64_t ad1 = desc_hi | (uint64_t)(x_lo + (cur.x >> 16));
-          const uint32_t d0 = tmem_base + (cur.y & 0xffffu);
-          const uint32_t nsg = (sg + 1 == kStages) ? 0 : sg + 1;
-          const uint32_t nwph = (sg + 1 == kStages) ? wph ^ 1 : wph;
-          const uint32_t nxr = (flags & kUStepEnd) ? xr + 1 : xr;
-          ready = issue_unit(d0, d0 + 256, ad0, ad1, bd, idesc, (flags & kUAccum) ? 1u : 0u,
-                             b_empty + sg * 8, (flags & kUCommitXFree) ? b_xfree : 0u,
-                             (flags & kUCommitAcc0) ? b_acc0 : ((flags & kUCommitAcc1) ? b_acc1 : 0u),
-                             b_full + nsg * 8, nwph, (nflags & kUWaitX0) ? b_x0 : 0u,
-                             (nflags & kUWaitX1) ? b_x1 : 0u, nxr & 1);
-          if (flags & (kUCommitAcc0 | kUCommitAcc1)) tr.ev(cur.z >> 16, (flags & kUCommitAcc0) ? 1 : 2);
+          if (++un >= u_end) un -= n_u;
+          const uint4 f0 = utab[2 * un], f1 = utab[2 * un + 1];
+          const uint32_t flags = c1.x, need = c1.y;
+          if ((ready & need) != need) {                    // slow path: something is not there yet
+            if ((need & 2) && !(ready & 2)) mbar_wait(&bars->x_ready[0], xr & 1);
+            if ((need & 4) && !(ready & 4)) mbar_wait(&bars->x_ready[1], xr & 1);
+            if (!(ready & 1)) mbar_wait(&bars->full[sg], wph);
+          }
+          const uint32_t nsg = (sg + 1) & (kStages - 1);
+          const uint32_t nwph = wph ^ (nsg == 0 ? 1u : 0u);
+          const uint32_t nxr = xr + ((flags & kUStepEnd) ? 1u : 0u);
+          const uint32_t d0 = tmem_base + c0.z;
+          ready = issue_unit(d0, d0 + 256, desc_hi | (uint64_t)(lo_base + c0.x),
+                             desc_hi | (uint64_t)(lo_base + c0.y),
+                             desc_hi | (uint64_t)(st_lo + sg * (kStageBytes >> 4)), c0.w,
+                             flags & kUAccum, b_empty + sg * 8, 0u, 0u, b_full + nsg * 8, nwph,
+                             (c1.z & 2) ? b_x0 : 0u, (c1.z & 4) ? b_x1 : 0u, nxr & 1);
+          if (flags & (kUWaitX0 | kUCommitXFree | kUCommitAcc0 | kUCommitAcc1)) {   // rare
+            if (flags & (kUCommitXFree | kUCommitAcc0 | kUCommitAcc1))
+              commit_optional((flags & kUCommitXFree) ? b_xfree : 0u,
+                              (flags & kUCommitAcc0) ? b_acc0 : ((flags & kUCommitAcc1) ? b_acc1 : 0u));
+            if (flags & kUWaitX0) tr.ev(c1.w, 0);
+            if (flags & (kUCommitAcc0 | kUCommitAcc1)) tr.ev(c1.w, (flags & kUCommitAcc0) ? 1 : 2);
+          }
           sg = nsg; wph = nwph; xr = nxr;
-          cur = nxt;
+          c0 = n0; c1 = n1; n0 = f0; n1 = f1;
         }
       }
       tr.finish(args, 0);
@@ -637,8 +644,9 @@ inline int build_tc_program(nfb_handle* h, int level, long long* wbytes, long lo
         const int b = t.src[kb];
         const int a0 = (b < kSrcIn) ? b * kABlockBytes : kXBytes;
         const int a1 = (b < kSrcIn) ? (4 + b) * kABlockBytes : kXBytes + kABlockBytes;
-        u.a0 = (uint16_t)(a0 >> 4); u.a1 = (uint16_t)(a1 >> 4);
-        u.dcol = (uint16_t)(c * t.chunk_n); u.chunk_n = (uint16_t)t.chunk_n; u.step = (uint16_t)si;
+        u.a0_lo = (uint32_t)(a0 >> 4); u.a1_lo = (uint32_t)(a1 >> 4);
+        u.dcol = (uint32_t)(c * t.chunk_n); u.idesc = make_idesc_bf16(kTileRows, t.chunk_n);
+        u.step = (uint32_t)si;
         if (kb) u.flags |= kUAccum;
         if (!have1 && (c == 1 || kb >= kb_need)) { u.flags |= kUWaitX1; have1 = true; }
         if (kb == t.nkb - 1) u.flags |= (c == 0 ? kUCommitAcc0 : kUCommitAcc1);
@@ -654,6 +662,16 @@ inline int build_tc_program(nfb_handle* h, int level, long long* wbytes, long lo
     prev_split = (t.n_chunks == 2) ? t.chunk_n / kBlockK : 99;
   }
   tp.unit_begin[tp.n_steps] = tp.n_units;
+  for (int i = 0; i < tp.n_units; ++i) {
+    TcUnit& u = tp.units[i];
+    u.need = 1u | ((u.flags & kUWaitX0) ? 2u : 0u) | ((u.flags & kUWaitX1) ? 4u : 0u);
+    // Successor in issue order.  After the last unit of a tile pair comes the first
+    // unit of the next pair, which (in every mode) waits for x_ready[0] only.
+    const bool last_of_pair = (i == tp.n_units - 1) || (tp.steps[u.step].epi == kEpiWarpHeads && (u.flags & kUStepEnd));
+    const uint32_t nf = (i + 1 < tp.n_units) ? tp.units[i + 1].flags : (uint32_t)kUWaitX0;
+    u.probe_next = ((nf & kUWaitX0) ? 2u : 0u) | ((nf & kUWaitX1) ? 4u : 0u);
+    (void)last_of_pair;
+  }
   return 0;
 }
 

@@ -437,14 +437,14 @@ int nfb_selftest_microbench(int mode, int n, int reps, int nwarps, long long* ou
   unsigned char* g = nullptr;
   NFB_CUDA(cudaMalloc(&d, 4 * sizeof(long long)));
   NFB_CUDA(cudaMemset(d, 0, 4 * sizeof(long long)));
-  NFB_CUDA(cudaMalloc(&g, 16384));
-  NFB_CUDA(cudaMemset(g, 0, 16384));
-  const int smem = 7 * 16384;
+  NFB_CUDA(cudaMalloc(&g, 8 * 16384));
+  NFB_CUDA(cudaMemset(g, 0, 8 * 16384));
+  const int smem = ((mode & 255) >= 4 && (mode & 255) <= 6) ? 224 * 1024 : 7 * 16384;
   NFB_CUDA(cudaFuncSetAttribute(tc_microbench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   // mode bits 9..: grid size minus one (chip-wide contention experiments)
   const int grid = (mode >> 9) + 1;
   mode &= 511;
-  tc_microbench_kernel<<<grid, 320, smem>>>(mode, n, reps, nwarps, d, g);
+  tc_microbench_kernel<<<grid, 320, smem>>>(mode, n, reps, nwarps, d, g, smem / 4);
   cudaError_t e = cudaDeviceSynchronize();
   cudaFree(g);
   if (e == cudaSuccess) e = cudaMemcpy(out, d, 3 * sizeof(long long), cudaMemcpyDeviceToHost);

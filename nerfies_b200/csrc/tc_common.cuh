@@ -236,8 +236,10 @@ __device__ __forceinline__ uint32_t issue_unit(uint32_t d0, uint32_t d1, uint64_
       "tcgen05.mma.cta_group::1.kind::f16 [%2], a12, b2, %6, pt;\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%2], a13, b3, %6, pt;\n\t"
       "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%8];\n\t"
-      "@pcx tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%9];\n\t"
-      "@pca tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%10];\n\t"
+      // A tcgen05.commit occupies an issue slot behind the MMAs (~120 cycles measured)
+      // even when predicated off: branch around the optional ones.
+      // (the optional x_free / acc_ready commits are issued by the caller through a
+      //  non-inlined call: ptxas if-converts a branch around them into predication)
       "selp.u32 %0, 1, 0, pw;\n\t"
       "selp.u32 t0, 2, 0, px0;\n\t"
       "selp.u32 t1, 4, 0, px1;\n\t"
@@ -250,6 +252,15 @@ __device__ __forceinline__ uint32_t issue_unit(uint32_t d0, uint32_t d1, uint64_
         "r"(par_x)
       : "memory");
   return out;
+}
+
+// Optional commits of a unit.  Deliberately not inlined: a call cannot be
+// if-converted, so units without these commits do not pay their issue slots.
+__device__ __noinline__ void commit_optional(uint32_t bar_xfree, uint32_t bar_acc) {
+  if (bar_xfree)
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_xfree) : "memory");
+  if (bar_acc)
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_acc) : "memory");
 }
 
 // ---- bf16 helpers ---------------------------------------------------------------

@@ -36,13 +36,17 @@ enum UnitFlags {
   kUCommitXFree = 32,   // commit x_free after this unit
   kUStepEnd = 64,       // last unit of its step
 };
+// Everything the issuer needs is precomputed on the host so that the single
+// issuing thread executes as few (serially dependent) instructions as possible
+// between two issue blocks.
 struct TcUnit {
-  uint16_t a0, a1;      // A operand of sub-tile 0/1: (byte offset from the activation base) >> 4
-  uint16_t dcol;        // accumulator column offset inside the sub-tile's 256 columns
-  uint16_t chunk_n;     // MMA N
-  uint16_t flags;
-  uint16_t step;
-  uint32_t pad;
+  uint32_t a0_lo, a1_lo;   // A descriptor low words of sub-tile 0/1, relative to the activation base
+  uint32_t dcol;           // accumulator column offset (sub-tile 0; sub-tile 1 = +256)
+  uint32_t idesc;          // tcgen05 instruction descriptor (M=128, N=chunk)
+  uint32_t flags;          // UnitFlags of this unit
+  uint32_t need;           // look-ahead bits that must be set before issuing: 1 weights | 2 x_ready[0] | 4 x_ready[1]
+  uint32_t probe_next;     // which x_ready barriers the NEXT unit (cyclically) needs: 2 | 4
+  uint32_t step;
 };
 
 struct TcProgram {

@@ -116,7 +116,7 @@ namespace nfb {
 namespace tc {
 
 __global__ void __launch_bounds__(320, 1)
-tc_microbench_kernel(int mode, int n, int reps, int nwarps, long long* out, const uint8_t* gsrc) {
+tc_microbench_kernel(int mode, int n, int reps, int nwarps, long long* out, const uint8_t* gsrc, int smem_words) {
   extern __shared__ __align__(1024) uint8_t raw[];   // 7 x 16 KB: A (2 half-blocks), B stages 1..4, scratch
   uint8_t* a_blk = raw;                       // 16 KB
   uint8_t* b_blk = raw + kABlockBytes;        // up to 32 KB
@@ -125,7 +125,7 @@ tc_microbench_kernel(int mode, int n, int reps, int nwarps, long long* out, cons
   __shared__ volatile int stop_flag;
   const int tid = threadIdx.x, warp = tid >> 5;
   if (tid == 0) stop_flag = 0;
-  for (int i = tid; i < 7 * 16384 / 4; i += blockDim.x)
+  for (int i = tid; i < smem_words; i += blockDim.x)
   {
     // small bf16 values: constant, or (mode bit 8) pseudo-random mantissas/signs
     uint32_t v = 0x3c003c00u;
@@ -203,7 +203,59 @@ tc_microbench_kernel(int mode, int n, int reps, int nwarps, long long* out, cons
       if (tid == 256) { out[0] = t2 - t0; out[1] = 8LL * reps; out[2] = t1 - t0; }
       stop_flag = 1;
     }
-  } else if (mode == 3) {
+  } else if (mode == 6) {
+    // Full replica of the fused kernel's weight ring: warp 9 streams 16 KB units
+    // (global -> shared, cp.async.bulk) through kRing stages with full/empty
+    // mbarriers; warp 8's elected lane consumes them with issue_unit() exactly as
+    // field_tc_kernel does (8 MMAs + commit to empty[stage] per unit).
+    constexpr int kRing = 4;
+    __shared__ uint64_t rfull[kRing], rempty[kRing];
+    if (tid == 0) {
+      for (int i = 0; i < kRing; ++i) { mbar_init(&rfull[i], 1); mbar_init(&rempty[i], 1); }
+      fence_barrier_init();
+    }
+    __syncthreads();
+    uint8_t* ring = raw + 160 * 1024;
+    const uint32_t unit_bytes = (uint32_t)n * kRowBytes;      // n = MMA N (64 or 128)
+    if (warp == 9) {
+      if (elect_one()) {
+        for (int it = 0; it < reps; ++it) {
+          const int sgp = it % kRing;
+          mbar_wait(&rempty[sgp], ((it / kRing) & 1) ^ 1);
+          mbar_arrive_expect_tx(&rfull[sgp], unit_bytes);
+          bulk_g2s(ring + sgp * 16384, gsrc + (size_t)(it & 7) * 16384, unit_bytes, &rfull[sgp]);
+        }
+      }
+      __syncwarp();
+    } else if (warp == 8) {
+      if (elect_one()) {
+        const uint32_t idesc = make_idesc_bf16(128, n);
+        const uint64_t hi = make_smem_desc(0);
+        const uint32_t base_lo = (smem_u32(raw) & 0x3FFFFu) >> 4;
+        const uint32_t st_lo = base_lo + (160 * 1024 >> 4);
+        const uint32_t bf = smem_u32(&rfull[0]), be = smem_u32(&rempty[0]);
+        uint32_t sg = 0, wph = 0, ready = 0;
+        const long long t0 = clock64();
+        for (int it = 0; it < reps; ++it) {
+          if (!(ready & 1)) mbar_wait(&rfull[sg], wph);
+          const uint32_t ablk = (it & 3) * 1024;
+          const uint64_t bd = hi | (uint64_t)(st_lo + sg * 1024);
+          const uint64_t ad0 = hi | (uint64_t)(base_lo + ablk), ad1 = hi | (uint64_t)(base_lo + ablk + 4096);
+          const uint32_t nsg = (sg + 1 == kRing) ? 0 : sg + 1;
+          const uint32_t nwph = (sg + 1 == kRing) ? wph ^ 1 : wph;
+          ready = issue_unit(tmem_base, tmem_base + 256, ad0, ad1, bd, idesc, 1u, be + sg * 8, 0u, 0u,
+                             bf + nsg * 8, nwph, 0u, 0u, 0u);
+          sg = nsg; wph = nwph;
+        }
+        umma_commit(&bar);
+        mbar_wait(&bar, 0);
+        const long long t2 = clock64();
+        out[0] = t2 - t0; out[1] = 8LL * reps; out[2] = 0;
+      }
+      __syncwarp();
+    }
+  } else if (mode >= 3 && mode <= 5) {
+    const int layout = mode - 3;
     // The current issuer: one elected-lane region per 4 units, barrier probed
     // between the 6th and 7th MMA of a unit.  Variant bits as in mode 2 (b4 bulk
     // copies, b5 tcgen05.ld from 8 warps) plus b2: smem st/ld traffic from warps 0-7.
@@ -248,7 +300,12 @@ tc_microbench_kernel(int mode, int n, int reps, int nwarps, long long* out, cons
     if (warp == 8) {
       const uint32_t idesc = make_idesc_bf16(128, n);
       const uint64_t hi = make_smem_desc(0);
-      const uint32_t a_lo = (smem_u32(a_blk) & 0x3FFFFu) >> 4, b_lo = (smem_u32(b_blk) & 0x3FFFFu) >> 4;
+      // layout: 0 = compact (A at 0 / +8 KB, B stages from 16 KB);
+      //         1 = the fused kernel's (A blocks at b*16 KB and (4+b)*16 KB, B stages from 160 KB)
+      const uint32_t base_lo = (smem_u32(raw) & 0x3FFFFu) >> 4;
+      const uint32_t a_lo = base_lo, b_lo = layout ? base_lo + (160 * 1024 >> 4) : base_lo + 1024;
+      const uint32_t a1_off = layout ? (64 * 1024 >> 4) : 512;
+      const uint32_t dchunk = layout >= 2 ? 128 : 0;
       const long long t0 = clock64();
       for (int r = 0; r < reps; r += 4) {
         if (elect_one()) {
@@ -257,16 +314,18 @@ tc_microbench_kernel(int mode, int n, int reps, int nwarps, long long* out, cons
             if (!ready) mbar_wait(&bar3, 1);
             tc_fence_after();
             const uint64_t bd = hi | (uint64_t)(b_lo + (u & 3) * 1024);
-            const uint64_t ad0 = hi | (uint64_t)a_lo, ad1 = hi | (uint64_t)(a_lo + 512);
-            umma_bf16(tmem_base, ad0, bd, idesc, 1u);
-            umma_bf16(tmem_base, ad0 + 2, bd + 2, idesc, 1u);
-            umma_bf16(tmem_base, ad0 + 4, bd + 4, idesc, 1u);
-            umma_bf16(tmem_base, ad0 + 6, bd + 6, idesc, 1u);
-            umma_bf16(tmem_base + 256, ad1, bd, idesc, 1u);
-            umma_bf16(tmem_base + 256, ad1 + 2, bd + 2, idesc, 1u);
+            const uint32_t ablk = layout ? (u & 3) * 1024 : 0;
+            const uint64_t ad0 = hi | (uint64_t)(a_lo + ablk), ad1 = hi | (uint64_t)(a_lo + ablk + a1_off);
+            const uint32_t dd = tmem_base + (((r >> 2) & 1) ? dchunk : 0);
+            umma_bf16(dd, ad0, bd, idesc, 1u);
+            umma_bf16(dd, ad0 + 2, bd + 2, idesc, 1u);
+            umma_bf16(dd, ad0 + 4, bd + 4, idesc, 1u);
+            umma_bf16(dd, ad0 + 6, bd + 6, idesc, 1u);
+            umma_bf16(dd + 256, ad1, bd, idesc, 1u);
+            umma_bf16(dd + 256, ad1 + 2, bd + 2, idesc, 1u);
             ready = mbar_test(&bar3, 1);
-            umma_bf16(tmem_base + 256, ad1 + 4, bd + 4, idesc, 1u);
-            umma_bf16(tmem_base + 256, ad1 + 6, bd + 6, idesc, 1u);
+            umma_bf16(dd + 256, ad1 + 4, bd + 4, idesc, 1u);
+            umma_bf16(dd + 256, ad1 + 6, bd + 6, idesc, 1u);
             umma_commit(&bar2);
           }
         }

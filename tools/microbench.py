@@ -21,7 +21,14 @@ for variant in (0, 52):
 for mode in (3, 3 + 256):
   _lib.check(lib.nfb_selftest_microbench(mode, 128, 512, 0, out))
   print(f'probe-ahead issuer N=128, {"random" if mode & 256 else "constant"} operand data: {out[0]/out[1]:.1f} cycles/MMA')
-for grid in (1, 2, 8, 74, 148):
+for mode, name in ((3, 'compact layout'), (4, 'fused-kernel layout (A blocks 16 KB apart, sub-tiles 64 KB apart, B at 160 KB+)'), (5, 'fused layout + alternating accumulator chunks')):
+  _lib.check(lib.nfb_selftest_microbench(mode, 128, 512, 0, out))
+  print(f'probe-ahead issuer N=128, {name}: {out[0]/out[1]:.1f} cycles/MMA')
+for n in (128, 64):
+  for grid in (1, 148):
+    _lib.check(lib.nfb_selftest_microbench(6 + ((grid - 1) << 9), n, 1024, 0, out))
+    print(f'ring replica (4 x 16 KB stages, real cp.async.bulk + full/empty barriers), N={n}, {grid} CTAs: {out[0]/out[1]:.1f} cycles/MMA = {8*out[0]/out[1]:.0f} cycles/unit')
+for grid in (1,):
   _lib.check(lib.nfb_selftest_microbench(3 + ((grid - 1) << 9), 128, 2048, 0, out))
   print(f'probe-ahead issuer N=128 on {grid} CTAs/SMs concurrently: {out[0]/out[1]:.1f} cycles/MMA (block 0)')
 for mode in (0, 256):

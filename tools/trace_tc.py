@@ -54,7 +54,9 @@ if len(starts) > 2:
         print('          step %2d  MMA  weight waits in segment: %d cycles, %d misses' % (r[1], r[4] >> 8, r[4] & 0xff)); continue
       if r[0] == 0 and 20 <= r[2] < 30: nm = 'MMA  segment begin c%d seg%d' % ((r[2] - 20) // 2, (r[2] - 20) % 2)
       elif r[0] == 0 and 30 <= r[2] < 40: nm = 'MMA  segment issued c%d seg%d' % ((r[2] - 30) // 2, (r[2] - 30) % 2)
-      elif r[0] == 3: nm = 'PROD copy issued unit %d' % r[2]
+      elif r[0] == 0 and r[2] in (50, 51): nm = 'MMA  unit issue begins (weights %s)' % ('ready' if r[2] == 51 else 'NOT ready -> blocking wait')
+      elif r[0] == 0 and r[2] in (52, 53): nm = 'MMA  unit issued (next weights %s)' % ('ready' if r[2] == 53 else 'not yet')
+      elif r[0] == 3: nm = 'PROD stage free -> copy issued, unit %d' % r[2]
       elif r[0] == 0 and r[2] >= 30: nm = 'MMA  got weights c%d kb%d' % ((r[2] - 30) // 8, (r[2] - 30) % 8)
       elif r[0] == 0 and r[2] >= 10: nm = 'MMA  wait weights c%d kb%d' % ((r[2] - 10) // 8, (r[2] - 10) % 8)
       else: nm = names[r[0]][r[2]]

@@ -34,7 +34,8 @@ constexpr int kInBytes = 2 * kABlockBytes;
 constexpr int kBiasBytes = 2 * 256 * 4;          // double-buffered per-step biases
 // No alignment slack: the dynamic shared-memory window of a kernel without static
 // shared memory starts 1024-byte aligned (checked at run time, trap otherwise).
-constexpr int kTcSmemBytes = kXBytes + kInBytes + kStages * kStageBytes + kBiasBytes + 128;
+constexpr int kAlphaBytes = 256 * 2;              // alpha-head weights, bf16
+constexpr int kTcSmemBytes = kXBytes + kInBytes + kStages * kStageBytes + kBiasBytes + kAlphaBytes + 128;
 constexpr int kPairRows = 2 * kTileRows;
 
 struct TcBars {
@@ -152,7 +153,7 @@ __device__ __noinline__ void posenc_fast_to_block(uint8_t* block, int r, const f
 // so relu-then-round == round-then-relu).
 __device__ __forceinline__ void epi_piece(const float* v, const float* __restrict__ bias32,
                                           bool relu, bool adot,
-                                          const float* __restrict__ alpha_w32, float& alpha,
+                                          const __nv_bfloat16* __restrict__ alpha_w32, float& alpha,
                                           uint32_t* out16) {
   float t[32];
 #pragma unroll
@@ -162,12 +163,16 @@ __device__ __forceinline__ void epi_piece(const float* v, const float* __restric
   }
   if (adot) {
 #pragma unroll
-    for (int j = 0; j < 32; j += 4) {
-      const float4 wq = __ldg(reinterpret_cast<const float4*>(alpha_w32 + j));
-      alpha = fmaf(fmaxf(t[j], 0.f), wq.x, alpha);
-      alpha = fmaf(fmaxf(t[j + 1], 0.f), wq.y, alpha);
-      alpha = fmaf(fmaxf(t[j + 2], 0.f), wq.z, alpha);
-      alpha = fmaf(fmaxf(t[j + 3], 0.f), wq.w, alpha);
+    for (int j = 0; j < 32; j += 8) {
+      // shared memory, broadcast: 8 bf16 weights per 128-bit load
+      const uint4 wq = *reinterpret_cast<const uint4*>(alpha_w32 + j);
+      const uint32_t w[4] = {wq.x, wq.y, wq.z, wq.w};
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float2 wf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[q]));
+        alpha = fmaf(fmaxf(t[j + 2 * q], 0.f), wf.x, alpha);
+        alpha = fmaf(fmaxf(t[j + 2 * q + 1], 0.f), wf.y, alpha);
+      }
     }
   }
   const __nv_bfloat162 zero = __float2bfloat162_rn(0.f);
@@ -207,7 +212,8 @@ field_tc_kernel(const __grid_constant__ TcProgram prog, const FieldArgs args,
   uint8_t* inbuf = xbuf + kXBytes;            // [2][16 KB]
   uint8_t* stages = inbuf + kInBytes;         // [kStages][16 KB]
   float* bias_s = reinterpret_cast<float*>(stages + kStages * kStageBytes);   // [2][256]
-  TcBars* bars = reinterpret_cast<TcBars*>(reinterpret_cast<uint8_t*>(bias_s) + kBiasBytes);
+  __nv_bfloat16* alpha_s = reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<uint8_t*>(bias_s) + kBiasBytes);
+  TcBars* bars = reinterpret_cast<TcBars*>(reinterpret_cast<uint8_t*>(alpha_s) + kAlphaBytes);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 256) {
@@ -326,6 +332,7 @@ field_tc_kernel(const __grid_constant__ TcProgram prog, const FieldArgs args,
     uint8_t* xs = xbuf + s * 4 * kABlockBytes;
     uint8_t* ins = inbuf + s * kABlockBytes;
     Tracer tr(args, (lane == 0 && (warp & 3) == 0) ? 1 + s : -1);
+    alpha_s[tid] = __float2bfloat16_rn(__ldg(aux + prog.alpha_w_off + tid));   // ordered by the first bar.sync
     uint32_t n_acc0 = 0, n_acc1 = 0, n_free = 0, n_step = 0;
     float next_bias = __ldg(aux + prog.steps[first_step].b_off + tid);
     RowState row;
@@ -386,7 +393,7 @@ field_tc_kernel(const __grid_constant__ TcProgram prog, const FieldArgs args,
         if (st.epi == kEpiHidden) {
           const int np = st.chunk_n / 32;              // 32-column pieces per chunk (2 or 4)
           const bool relu = st.relu != 0, adot = st.alpha_dot != 0;
-          const float* aw = aux + prog.alpha_w_off;
+          const __nv_bfloat16* aw = alpha_s;
           // ---- chunk 0: results are held in registers until the MMAs of chunk 1
           //      no longer read the blocks they overwrite ----
           uint32_t packed[64];

@@ -221,9 +221,6 @@ __device__ __forceinline__ uint32_t issue_unit(uint32_t d0, uint32_t d1, uint64_
       "setp.ne.b32 pca, %10, 0;\n\t"
       "setp.eq.b32 px0, 1, 0;\n\t"
       "setp.eq.b32 px1, 1, 0;\n\t"
-      "mbarrier.test_wait.parity.shared::cta.b64 pw, [%11], %12;\n\t"
-      "@pd0 mbarrier.test_wait.parity.shared::cta.b64 px0, [%13], %15;\n\t"
-      "@pd1 mbarrier.test_wait.parity.shared::cta.b64 px1, [%14], %15;\n\t"
       "add.u64 a01, %3, 2;\n\t add.u64 a02, %3, 4;\n\t add.u64 a03, %3, 6;\n\t"
       "add.u64 a11, %4, 2;\n\t add.u64 a12, %4, 4;\n\t add.u64 a13, %4, 6;\n\t"
       "add.u64 b1, %5, 2;\n\t add.u64 b2, %5, 4;\n\t add.u64 b3, %5, 6;\n\t"
@@ -233,6 +230,11 @@ __device__ __forceinline__ uint32_t issue_unit(uint32_t d0, uint32_t d1, uint64_
       "tcgen05.mma.cta_group::1.kind::f16 [%1], a03, b3, %6, pt;\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%2], %4, %5, %6, pacc;\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%2], a11, b1, %6, pt;\n\t"
+      // probes as late as their ~150-cycle latency allows: two MMAs (128 cycles of
+      // queue) still follow, and the later the probe the likelier the copy has landed
+      "mbarrier.test_wait.parity.shared::cta.b64 pw, [%11], %12;\n\t"
+      "@pd0 mbarrier.test_wait.parity.shared::cta.b64 px0, [%13], %15;\n\t"
+      "@pd1 mbarrier.test_wait.parity.shared::cta.b64 px1, [%14], %15;\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%2], a12, b2, %6, pt;\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%2], a13, b3, %6, pt;\n\t"
       "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%8];\n\t"

@@ -336,8 +336,12 @@ def nerf_mlp(params: Dict[str, Any], spec: OracleSpec, x: Tensor,
   else:
     alpha_input = h
   if alpha_condition is None:
-    # (the tensor-core path evaluates this Dense(1) in fp32 on CUDA cores)
-    alpha = dense(params['MLP_2']['logit'], alpha_input, exact=True)
+    # (the tensor-core path evaluates this Dense(1) on CUDA cores: fp32 activations,
+    #  bf16-rounded weights, fp32 accumulation)
+    pl = params['MLP_2']['logit']
+    if _BF16_OPERANDS:
+      pl = {'kernel': pl['kernel'].bfloat16().to(pl['kernel'].dtype), 'bias': pl['bias']}
+    alpha = dense(pl, alpha_input, exact=True)
   else:
     alpha = mlp(params['MLP_2'], alpha_input, 0, (), spec.activation,
                 has_logit=True)

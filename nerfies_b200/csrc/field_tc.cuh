@@ -82,7 +82,7 @@ struct RowState {
 };
 
 // [x | w_k * sin/cos features | extra | 0...] -> one 64-column K-block row.
-__device__ __noinline__ void posenc_to_block(uint8_t* block, int r, const float* x, int F,
+__device__ __forceinline__ void posenc_to_block(uint8_t* block, int r, const float* x, int F,
                                              const float* __restrict__ window,
                                              const float* __restrict__ extra, int n_extra) {
   const int nf = 6 * F;
@@ -112,7 +112,7 @@ __device__ __noinline__ void posenc_to_block(uint8_t* block, int r, const float*
 // reach the tensor cores, so the octave recurrence
 //   sin 2a = 2 sin a cos a,  cos 2a = 1 - 2 sin^2 a
 // (error doubles per octave: < 1e-4 at 2^9) replaces 6F libm calls by 3 sincosf.
-__device__ __noinline__ void posenc_fast_to_block(uint8_t* block, int r, const float* x, int F,
+__device__ __forceinline__ void posenc_fast_to_block(uint8_t* block, int r, const float* x, int F,
                                                   const float* __restrict__ window,
                                                   const float* __restrict__ extra, int n_extra) {
   float feat[64];
@@ -305,18 +305,22 @@ field_tc_kernel(const __grid_constant__ TcProgram prog, const FieldArgs args,
           const uint32_t nwph = wph ^ (nsg == 0 ? 1u : 0u);
           const uint32_t nxr = xr + ((flags & kUStepEnd) ? 1u : 0u);
           const uint32_t d0 = tmem_base + c0.z;
-          ready = issue_unit(d0, d0 + 256, desc_hi | (uint64_t)(lo_base + c0.x),
-                             desc_hi | (uint64_t)(lo_base + c0.y),
-                             desc_hi | (uint64_t)(st_lo + sg * (kStageBytes >> 4)), c0.w,
-                             flags & kUAccum, b_empty + sg * 8, 0u, 0u, b_full + nsg * 8, nwph,
-                             (c1.z & 2) ? b_x0 : 0u, (c1.z & 4) ? b_x1 : 0u, nxr & 1);
-          if (flags & (kUWaitX0 | kUCommitXFree | kUCommitAcc0 | kUCommitAcc1)) {   // rare
-            if (flags & (kUCommitXFree | kUCommitAcc0 | kUCommitAcc1))
-              commit_optional((flags & kUCommitXFree) ? b_xfree : 0u,
-                              (flags & kUCommitAcc0) ? b_acc0 : ((flags & kUCommitAcc1) ? b_acc1 : 0u));
-            if (flags & kUWaitX0) tr.ev(c1.w, 0);
+          const uint64_t ad0 = desc_hi | (uint64_t)(lo_base + c0.x), ad1 = desc_hi | (uint64_t)(lo_base + c0.y);
+          const uint64_t bd = desc_hi | (uint64_t)(st_lo + sg * (kStageBytes >> 4));
+          const uint32_t px0 = (c1.z & 2) ? b_x0 : 0u, px1 = (c1.z & 4) ? b_x1 : 0u;
+          // Two inlined variants (no calls in this kernel: with the L1 carved out for
+          // shared memory an ABI spill around a call costs an L2 round trip).
+          if (flags & (kUCommitXFree | kUCommitAcc0 | kUCommitAcc1)) {
+            ready = issue_unit<true>(d0, d0 + 256, ad0, ad1, bd, c0.w, flags & kUAccum, b_empty + sg * 8,
+                                     (flags & kUCommitXFree) ? b_xfree : 0u,
+                                     (flags & kUCommitAcc0) ? b_acc0 : ((flags & kUCommitAcc1) ? b_acc1 : 0u),
+                                     b_full + nsg * 8, nwph, px0, px1, nxr & 1);
             if (flags & (kUCommitAcc0 | kUCommitAcc1)) tr.ev(c1.w, (flags & kUCommitAcc0) ? 1 : 2);
+          } else {
+            ready = issue_unit<false>(d0, d0 + 256, ad0, ad1, bd, c0.w, flags & kUAccum, b_empty + sg * 8,
+                                      0u, 0u, b_full + nsg * 8, nwph, px0, px1, nxr & 1);
           }
+          if (flags & kUWaitX0) tr.ev(c1.w, 0);
           sg = nsg; wph = nwph; xr = nxr;
           c0 = n0; c1 = n1; n0 = f0; n1 = f1;
         }

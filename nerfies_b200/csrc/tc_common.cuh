@@ -201,6 +201,7 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
 // here it is in flight while the MMAs queue.
 //   bar_* are shared-memory addresses (0 = skip); returns bit0/1/2 = the probed
 //   weight / x_ready[0] / x_ready[1] phase is complete.
+template <bool kOptionalCommits>
 __device__ __forceinline__ uint32_t issue_unit(uint32_t d0, uint32_t d1, uint64_t ad0, uint64_t ad1,
                                                uint64_t bd, uint32_t idesc, uint32_t accumulate,
                                                uint32_t bar_empty, uint32_t bar_xfree,
@@ -240,8 +241,8 @@ __device__ __forceinline__ uint32_t issue_unit(uint32_t d0, uint32_t d1, uint64_
       "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%8];\n\t"
       // A tcgen05.commit occupies an issue slot behind the MMAs (~120 cycles measured)
       // even when predicated off: branch around the optional ones.
-      // (the optional x_free / acc_ready commits are issued by the caller through a
-      //  non-inlined call: ptxas if-converts a branch around them into predication)
+      "@pcx tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%9];\n\t"
+      "@pca tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%10];\n\t"
       "selp.u32 %0, 1, 0, pw;\n\t"
       "selp.u32 t0, 2, 0, px0;\n\t"
       "selp.u32 t1, 4, 0, px1;\n\t"
@@ -254,15 +255,6 @@ __device__ __forceinline__ uint32_t issue_unit(uint32_t d0, uint32_t d1, uint64_
         "r"(par_x)
       : "memory");
   return out;
-}
-
-// Optional commits of a unit.  Deliberately not inlined: a call cannot be
-// if-converted, so units without these commits do not pay their issue slots.
-__device__ __noinline__ void commit_optional(uint32_t bar_xfree, uint32_t bar_acc) {
-  if (bar_xfree)
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_xfree) : "memory");
-  if (bar_acc)
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_acc) : "memory");
 }
 
 // ---- bf16 helpers ---------------------------------------------------------------

@@ -243,7 +243,7 @@ tc_microbench_kernel(int mode, int n, int reps, int nwarps, long long* out, cons
           const uint64_t ad0 = hi | (uint64_t)(base_lo + ablk), ad1 = hi | (uint64_t)(base_lo + ablk + 4096);
           const uint32_t nsg = (sg + 1 == kRing) ? 0 : sg + 1;
           const uint32_t nwph = (sg + 1 == kRing) ? wph ^ 1 : wph;
-          ready = issue_unit(tmem_base, tmem_base + 256, ad0, ad1, bd, idesc, 1u, be + sg * 8, 0u, 0u,
+          ready = issue_unit<false>(tmem_base, tmem_base + 256, ad0, ad1, bd, idesc, 1u, be + sg * 8, 0u, 0u,
                              bf + nsg * 8, nwph, 0u, 0u, 0u);
           sg = nsg; wph = nwph;
         }

@@ -25,6 +25,10 @@ _lib.check(hd.lib.nfb_render_samples(hd.h, 0, B, 128, _ptr(z), _ptr(rays['origin
 torch.cuda.synchronize()
 hd.lib.nfb_set_trace(hd.h, None, 0)
 t = buf.cpu().tolist()
+tot = t[4 + 2 * cap - 5:4 + 2 * cap]
+if tot[0]:
+  print('issuer totals: units %d, wall %.0f cyc/unit, inside issue_unit %.0f, slow-path waits %.0f, optional commits+trace %.0f, other %.0f' % (
+      tot[0], tot[1] / tot[0], tot[2] / tot[0], tot[3] / tot[0], tot[4] / tot[0], (tot[1] - tot[2] - tot[3] - tot[4]) / tot[0]))
 per = cap // 4
 recs = []
 for role in range(4):

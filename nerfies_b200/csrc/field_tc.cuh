@@ -293,32 +293,32 @@ field_tc_kernel(const __grid_constant__ TcProgram prog, const FieldArgs args,
       uint4 n0 = utab[2 * un], n1 = utab[2 * un + 1];
       for (int pair = blockIdx.x; pair < num_pairs; pair += gridDim.x) {
         for (int u = u_begin; u < u_end; ++u) {
-          if (++un >= u_end) un -= n_u;
-          const uint4 f0 = utab[2 * un], f1 = utab[2 * un + 1];
           const uint32_t flags = c1.x, need = c1.y;
           if ((ready & need) != need) {                    // slow path: something is not there yet
             if ((need & 2) && !(ready & 2)) mbar_wait(&bars->x_ready[0], xr & 1);
             if ((need & 4) && !(ready & 4)) mbar_wait(&bars->x_ready[1], xr & 1);
             if (!(ready & 1)) mbar_wait(&bars->full[sg], wph);
           }
+          const uint32_t d0 = tmem_base + c0.z;
+          const uint64_t bd = desc_hi | (uint64_t)(st_lo + sg * (kStageBytes >> 4));
+          issue_half0(d0, desc_hi | (uint64_t)(lo_base + c0.x), bd, c0.w, flags & kUAccum);
+          // ---- bookkeeping while sub-tile 0's MMAs execute ----
+          if (++un >= u_end) un -= n_u;
+          const uint4 f0 = utab[2 * un], f1 = utab[2 * un + 1];     // table entry two units ahead
           const uint32_t nsg = (sg + 1) & (kStages - 1);
           const uint32_t nwph = wph ^ (nsg == 0 ? 1u : 0u);
           const uint32_t nxr = xr + ((flags & kUStepEnd) ? 1u : 0u);
-          const uint32_t d0 = tmem_base + c0.z;
-          const uint64_t ad0 = desc_hi | (uint64_t)(lo_base + c0.x), ad1 = desc_hi | (uint64_t)(lo_base + c0.y);
-          const uint64_t bd = desc_hi | (uint64_t)(st_lo + sg * (kStageBytes >> 4));
+          const uint64_t ad1 = desc_hi | (uint64_t)(lo_base + c0.y);
           const uint32_t px0 = (c1.z & 2) ? b_x0 : 0u, px1 = (c1.z & 4) ? b_x1 : 0u;
-          // Two inlined variants (no calls in this kernel: with the L1 carved out for
-          // shared memory an ABI spill around a call costs an L2 round trip).
           if (flags & (kUCommitXFree | kUCommitAcc0 | kUCommitAcc1)) {
-            ready = issue_unit<true>(d0, d0 + 256, ad0, ad1, bd, c0.w, flags & kUAccum, b_empty + sg * 8,
-                                     (flags & kUCommitXFree) ? b_xfree : 0u,
-                                     (flags & kUCommitAcc0) ? b_acc0 : ((flags & kUCommitAcc1) ? b_acc1 : 0u),
-                                     b_full + nsg * 8, nwph, px0, px1, nxr & 1);
+            ready = issue_half1<true>(d0 + 256, ad1, bd, c0.w, flags & kUAccum, b_empty + sg * 8,
+                                      (flags & kUCommitXFree) ? b_xfree : 0u,
+                                      (flags & kUCommitAcc0) ? b_acc0 : ((flags & kUCommitAcc1) ? b_acc1 : 0u),
+                                      b_full + nsg * 8, nwph, px0, px1, nxr & 1);
             if (flags & (kUCommitAcc0 | kUCommitAcc1)) tr.ev(c1.w, (flags & kUCommitAcc0) ? 1 : 2);
           } else {
-            ready = issue_unit<false>(d0, d0 + 256, ad0, ad1, bd, c0.w, flags & kUAccum, b_empty + sg * 8,
-                                      0u, 0u, b_full + nsg * 8, nwph, px0, px1, nxr & 1);
+            ready = issue_half1<false>(d0 + 256, ad1, bd, c0.w, flags & kUAccum, b_empty + sg * 8, 0u, 0u,
+                                       b_full + nsg * 8, nwph, px0, px1, nxr & 1);
           }
           if (flags & kUWaitX0) tr.ev(c1.w, 0);
           sg = nsg; wph = nwph; xr = nxr;

@@ -257,6 +257,76 @@ __device__ __forceinline__ uint32_t issue_unit(uint32_t d0, uint32_t d1, uint64_
   return out;
 }
 
+// First half of a unit: fence + the 4 MMAs of sub-tile 0.  The caller does its
+// loop bookkeeping between issue_half0() and issue_half1(): the thread is not
+// needed while these MMAs execute, and the tensor queue is too shallow to bridge
+// a gap *between* units.
+__device__ __forceinline__ void issue_half0(uint32_t d0, uint64_t ad0, uint64_t bd, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred pacc, pt;\n\t"
+      ".reg .b64 a1, a2, a3, b1, b2, b3;\n\t"
+      "tcgen05.fence::after_thread_sync;\n\t"
+      "setp.ne.b32 pacc, %4, 0;\n\t"
+      "setp.eq.b32 pt, 0, 0;\n\t"
+      "add.u64 a1, %1, 2;\n\t add.u64 a2, %1, 4;\n\t add.u64 a3, %1, 6;\n\t"
+      "add.u64 b1, %2, 2;\n\t add.u64 b2, %2, 4;\n\t add.u64 b3, %2, 6;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, pacc;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], a1, b1, %3, pt;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], a2, b2, %3, pt;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], a3, b3, %3, pt;\n\t"
+      "}"
+      ::"r"(d0), "l"(ad0), "l"(bd), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// Second half: look-ahead probes, the 4 MMAs of sub-tile 1, commits; returns the
+// probe bits (see issue_unit).
+template <bool kOptionalCommits>
+__device__ __forceinline__ uint32_t issue_half1(uint32_t d1, uint64_t ad1, uint64_t bd, uint32_t idesc,
+                                                uint32_t accumulate, uint32_t bar_empty,
+                                                uint32_t bar_xfree, uint32_t bar_acc, uint32_t probe_w,
+                                                uint32_t par_w, uint32_t probe_x0, uint32_t probe_x1,
+                                                uint32_t par_x) {
+  uint32_t out;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred pacc, pt, pw, px0, px1, pd0, pd1, pcx, pca;\n\t"
+      ".reg .b64 a1, a2, a3, b1, b2, b3;\n\t"
+      ".reg .b32 t0, t1;\n\t"
+      "setp.ne.b32 pacc, %5, 0;\n\t"
+      "setp.eq.b32 pt, 0, 0;\n\t"
+      "setp.ne.b32 pd0, %11, 0;\n\t"
+      "setp.ne.b32 pd1, %12, 0;\n\t"
+      "setp.ne.b32 pcx, %7, 0;\n\t"
+      "setp.ne.b32 pca, %8, 0;\n\t"
+      "setp.eq.b32 px0, 1, 0;\n\t"
+      "setp.eq.b32 px1, 1, 0;\n\t"
+      "add.u64 a1, %2, 2;\n\t add.u64 a2, %2, 4;\n\t add.u64 a3, %2, 6;\n\t"
+      "add.u64 b1, %3, 2;\n\t add.u64 b2, %3, 4;\n\t add.u64 b3, %3, 6;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%1], %2, %3, %4, pacc;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%1], a1, b1, %4, pt;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 pw, [%9], %10;\n\t"
+      "@pd0 mbarrier.test_wait.parity.shared::cta.b64 px0, [%11], %13;\n\t"
+      "@pd1 mbarrier.test_wait.parity.shared::cta.b64 px1, [%12], %13;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%1], a2, b2, %4, pt;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%1], a3, b3, %4, pt;\n\t"
+      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%6];\n\t"
+      "@pcx tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%7];\n\t"
+      "@pca tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%8];\n\t"
+      "selp.u32 %0, 1, 0, pw;\n\t"
+      "selp.u32 t0, 2, 0, px0;\n\t"
+      "selp.u32 t1, 4, 0, px1;\n\t"
+      "or.b32 %0, %0, t0;\n\t"
+      "or.b32 %0, %0, t1;\n\t"
+      "}"
+      : "=r"(out)
+      : "r"(d1), "l"(ad1), "l"(bd), "r"(idesc), "r"(accumulate), "r"(bar_empty), "r"(bar_xfree),
+        "r"(bar_acc), "r"(probe_w), "r"(par_w), "r"(probe_x0), "r"(probe_x1), "r"(par_x)
+      : "memory");
+  return out;
+}
+
 // ---- bf16 helpers ---------------------------------------------------------------
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);

@@ -25,10 +25,12 @@ _lib.check(hd.lib.nfb_render_samples(hd.h, 0, B, 128, _ptr(z), _ptr(rays['origin
 torch.cuda.synchronize()
 hd.lib.nfb_set_trace(hd.h, None, 0)
 t = buf.cpu().tolist()
-tot = t[4 + 2 * cap - 5:4 + 2 * cap]
-if tot[0]:
-  print('issuer totals: units %d, wall %.0f cyc/unit, inside issue_unit %.0f, slow-path waits %.0f, optional commits+trace %.0f, other %.0f' % (
-      tot[0], tot[1] / tot[0], tot[2] / tot[0], tot[3] / tot[0], tot[4] / tot[0], (tot[1] - tot[2] - tot[3] - tot[4]) / tot[0]))
+o = t[4 + 2 * cap - 10:4 + 2 * cap]
+if o[0]:
+  n = o[3] + o[5] + o[7]
+  print('issuer accounting: wall %.0f cyc/unit over %d units; waits+probe-miss %.0f/unit;' % (o[0] / n, n, o[1] / n))
+  for name, i in (('N=128', 0), ('N=64', 1), ('N=16', 2)):
+    if o[3 + 2 * i]: print('   %s units: %d, inside issue block %.0f cycles each' % (name, o[3 + 2 * i], o[2 + 2 * i] / o[3 + 2 * i]))
 per = cap // 4
 recs = []
 for role in range(4):

@@ -291,6 +291,11 @@ field_tc_kernel(const __grid_constant__ TcProgram prog, const FieldArgs args,
       uint4 c0 = utab[2 * u_begin], c1 = utab[2 * u_begin + 1];
       int un = u_begin + (1 % n_u);
       uint4 n0 = utab[2 * un], n1 = utab[2 * un + 1];
+      // operands of the unit about to issue (computed one unit ahead, in the
+      // bookkeeping window between the two issue blocks)
+      uint32_t d0 = tmem_base + c0.z;
+      uint64_t bd = desc_hi | (uint64_t)st_lo;
+      uint64_t ad0 = desc_hi | (uint64_t)(lo_base + c0.x);
       for (int pair = blockIdx.x; pair < num_pairs; pair += gridDim.x) {
         for (int u = u_begin; u < u_end; ++u) {
           const uint32_t flags = c1.x, need = c1.y;
@@ -299,9 +304,7 @@ field_tc_kernel(const __grid_constant__ TcProgram prog, const FieldArgs args,
             if ((need & 4) && !(ready & 4)) mbar_wait(&bars->x_ready[1], xr & 1);
             if (!(ready & 1)) mbar_wait(&bars->full[sg], wph);
           }
-          const uint32_t d0 = tmem_base + c0.z;
-          const uint64_t bd = desc_hi | (uint64_t)(st_lo + sg * (kStageBytes >> 4));
-          issue_half0(d0, desc_hi | (uint64_t)(lo_base + c0.x), bd, c0.w, flags & kUAccum);
+          issue_half0(d0, ad0, bd, c0.w, flags & kUAccum);
           // ---- bookkeeping while sub-tile 0's MMAs execute ----
           if (++un >= u_end) un -= n_u;
           const uint4 f0 = utab[2 * un], f1 = utab[2 * un + 1];     // table entry two units ahead
@@ -310,14 +313,20 @@ field_tc_kernel(const __grid_constant__ TcProgram prog, const FieldArgs args,
           const uint32_t nxr = xr + ((flags & kUStepEnd) ? 1u : 0u);
           const uint64_t ad1 = desc_hi | (uint64_t)(lo_base + c0.y);
           const uint32_t px0 = (c1.z & 2) ? b_x0 : 0u, px1 = (c1.z & 4) ? b_x1 : 0u;
+          const uint32_t d1 = d0 + 256, idesc = c0.w, bar_e = b_empty + sg * 8;
+          const uint64_t bd_cur = bd;
+          // next unit's first-half operands
+          d0 = tmem_base + n0.z;
+          bd = desc_hi | (uint64_t)(st_lo + nsg * (kStageBytes >> 4));
+          ad0 = desc_hi | (uint64_t)(lo_base + n0.x);
           if (flags & (kUCommitXFree | kUCommitAcc0 | kUCommitAcc1)) {
-            ready = issue_half1<true>(d0 + 256, ad1, bd, c0.w, flags & kUAccum, b_empty + sg * 8,
+            ready = issue_half1<true>(d1, ad1, bd_cur, idesc, flags & kUAccum, bar_e,
                                       (flags & kUCommitXFree) ? b_xfree : 0u,
                                       (flags & kUCommitAcc0) ? b_acc0 : ((flags & kUCommitAcc1) ? b_acc1 : 0u),
                                       b_full + nsg * 8, nwph, px0, px1, nxr & 1);
             if (flags & (kUCommitAcc0 | kUCommitAcc1)) tr.ev(c1.w, (flags & kUCommitAcc0) ? 1 : 2);
           } else {
-            ready = issue_half1<false>(d0 + 256, ad1, bd, c0.w, flags & kUAccum, b_empty + sg * 8, 0u, 0u,
+            ready = issue_half1<false>(d1, ad1, bd_cur, idesc, flags & kUAccum, bar_e, 0u, 0u,
                                        b_full + nsg * 8, nwph, px0, px1, nxr & 1);
           }
           if (flags & kUWaitX0) tr.ev(c1.w, 0);

@@ -28,7 +28,9 @@ namespace tc {
 
 constexpr int kStages = 4;
 constexpr int kStageBytes = 16384;              // 128 rows x 128 B
-constexpr int kTcThreads = 320;
+constexpr int kTcThreads = 320;                 // 8 epilogue warps (+ issuer, producer)
+constexpr int kTcThreads16 = 576;               // 16 epilogue warps
+constexpr int kDefaultEpiWarps = 8;
 constexpr int kXBytes = 2 * 4 * kABlockBytes;   // 2 sub-tiles x 4 K-blocks
 constexpr int kInBytes = 2 * kABlockBytes;
 constexpr int kBiasBytes = 2 * 256 * 4;          // double-buffered per-step biases
@@ -84,10 +86,11 @@ struct RowState {
 // [x | w_k * sin/cos features | extra | 0...] -> one 64-column K-block row.
 __device__ __forceinline__ void posenc_to_block(uint8_t* block, int r, const float* x, int F,
                                              const float* __restrict__ window,
-                                             const float* __restrict__ extra, int n_extra) {
+                                             const float* __restrict__ extra, int n_extra,
+                                             int c_begin = 0, int c_end = 8) {
   const int nf = 6 * F;
 #pragma unroll 1
-  for (int c = 0; c < 8; ++c) {
+  for (int c = c_begin; c < c_end; ++c) {
     float v[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -114,7 +117,8 @@ __device__ __forceinline__ void posenc_to_block(uint8_t* block, int r, const flo
 // (error doubles per octave: < 1e-4 at 2^9) replaces 6F libm calls by 3 sincosf.
 __device__ __forceinline__ void posenc_fast_to_block(uint8_t* block, int r, const float* x, int F,
                                                   const float* __restrict__ window,
-                                                  const float* __restrict__ extra, int n_extra) {
+                                                  const float* __restrict__ extra, int n_extra,
+                                                  int c_begin = 0, int c_end = 8) {
   float feat[64];
 #pragma unroll
   for (int k = 0; k < 64; ++k) feat[k] = 0.f;
@@ -145,7 +149,8 @@ __device__ __forceinline__ void posenc_fast_to_block(uint8_t* block, int r, cons
     if (k >= d && k < d + n_extra) feat[k] = __ldg(extra + (k - d));
   }
 #pragma unroll
-  for (int c = 0; c < 8; ++c) store_chunk(block, r, c, feat + c * 8);
+  for (int c = 0; c < 8; ++c)
+    if (c >= c_begin && c < c_end) store_chunk(block, r, c, feat + c * 8);
 }
 
 // One 32-column piece of a hidden layer's epilogue: + bias, (alpha head dot),
@@ -185,9 +190,9 @@ __device__ __forceinline__ void epi_piece(const float* v, const float* __restric
 }
 
 __device__ __forceinline__ void cond_to_block(uint8_t* block, int r, const float* __restrict__ cond,
-                                              int n) {
+                                              int n, int c_begin = 0, int c_end = 8) {
 #pragma unroll 1
-  for (int c = 0; c < 8; ++c) {
+  for (int c = c_begin; c < c_end; ++c) {
     float v[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -198,10 +203,16 @@ __device__ __forceinline__ void cond_to_block(uint8_t* block, int r, const float
   }
 }
 
-__global__ void __launch_bounds__(kTcThreads, 1)
+// kH = epilogue threads per row: 1 (8 epilogue warps) or 2 (16 warps; the two
+// threads of a row are in warps w and w+4 - same TMEM lane quarter - and split
+// every chunk's columns; the per-row scalar work is done redundantly by both).
+template <int kH>
+__global__ void __launch_bounds__(32 * (8 * kH + 2), 1)
 field_tc_kernel(const __grid_constant__ TcProgram prog, const FieldArgs args,
                 const uint8_t* __restrict__ wpack, const float* __restrict__ aux,
                 int num_pairs) {
+  constexpr int kEpiWarps = 8 * kH, kMmaWarp = kEpiWarps, kProdWarp = kEpiWarps + 1;
+  constexpr int kEpiThreads = 256 * kH;
   extern __shared__ __align__(1024) uint8_t raw[];
   uint8_t* base = raw;
   if ((smem_u32(base) & 1023u) != 0) {
@@ -216,14 +227,14 @@ field_tc_kernel(const __grid_constant__ TcProgram prog, const FieldArgs args,
   TcBars* bars = reinterpret_cast<TcBars*>(reinterpret_cast<uint8_t*>(alpha_s) + kAlphaBytes);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  if (tid == 256) {
+  if (tid == kMmaWarp * 32) {
     for (int i = 0; i < kStages; ++i) { mbar_init(&bars->full[i], 1); mbar_init(&bars->empty[i], 1); }
     mbar_init(&bars->acc_ready[0], 1); mbar_init(&bars->acc_ready[1], 1);
     mbar_init(&bars->x_free, 1);
-    mbar_init(&bars->x_ready[0], 256); mbar_init(&bars->x_ready[1], 256);
+    mbar_init(&bars->x_ready[0], kEpiThreads); mbar_init(&bars->x_ready[1], kEpiThreads);
     fence_barrier_init();
   }
-  if (warp == 8) tmem_alloc(&bars->tmem_slot, 512);
+  if (warp == kMmaWarp) tmem_alloc(&bars->tmem_slot, 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -241,7 +252,7 @@ field_tc_kernel(const __grid_constant__ TcProgram prog, const FieldArgs args,
     while (prog.steps[last_step].epi != kEpiWarpHeads) ++last_step;
   }
 
-  if (warp == 9) {
+  if (warp == kProdWarp) {
     // ===================== weight producer =====================
     // (the whole warp runs the loop; one elected lane issues the copies)
     {
@@ -267,7 +278,7 @@ field_tc_kernel(const __grid_constant__ TcProgram prog, const FieldArgs args,
       }
       if (lane == 0) tr.finish(args, 3);
     }
-  } else if (warp == 8) {
+  } else if (warp == kMmaWarp) {
     // ===================== MMA issuer =====================
     // One elected lane walks the flattened, host-precomputed schedule (TcUnit).
     // Per unit: one issue_unit() block (fence, look-ahead probes of the next unit's
@@ -338,18 +349,23 @@ field_tc_kernel(const __grid_constant__ TcProgram prog, const FieldArgs args,
     }
     __syncwarp();
   } else {
-    // ===================== epilogue: one thread per row =====================
-    const int s = warp >> 2;                           // sub-tile
-    const int r = (warp & 3) * 32 + lane;              // row within the sub-tile
-    const uint32_t t_lane = tmem_base + (((uint32_t)(warp & 3) * 32) << 16) + s * 256;
+    // ===================== epilogue: kH threads per row =====================
+    const int s = warp / (4 * kH);                     // sub-tile
+    const int hs = (warp >> 2) & (kH - 1);             // which column half of a chunk (kH = 2)
+    const int qd = warp & 3;                           // TMEM lane quarter
+    const int r = qd * 32 + lane;                      // row within the sub-tile
+    const uint32_t t_lane = tmem_base + (((uint32_t)qd * 32) << 16) + s * 256;
     uint8_t* xs = xbuf + s * 4 * kABlockBytes;
     uint8_t* ins = inbuf + s * kABlockBytes;
-    Tracer tr(args, (lane == 0 && (warp & 3) == 0) ? 1 + s : -1);
-    alpha_s[tid] = __float2bfloat16_rn(__ldg(aux + prog.alpha_w_off + tid));   // ordered by the first bar.sync
+    const int cb = hs * (8 / kH), ce = cb + 8 / kH;    // input-block chunks this thread writes
+    Tracer tr(args, (lane == 0 && qd == 0 && hs == 0) ? 1 + s : -1);
+    if (tid < 256) alpha_s[tid] = __float2bfloat16_rn(__ldg(aux + prog.alpha_w_off + tid));   // ordered by the first bar.sync
     uint32_t n_acc0 = 0, n_acc1 = 0, n_free = 0, n_step = 0;
-    float next_bias = __ldg(aux + prog.steps[first_step].b_off + tid);
+    float next_bias = tid < 256 ? __ldg(aux + prog.steps[first_step].b_off + tid) : 0.f;
+    bool merge_alpha = false;                          // kH = 2: partner's alpha partial is waiting
     RowState row;
     const int S = args.samples_per_ray;
+    auto epi_sync = [&]() { asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory"); };
 
     auto arrive_both = [&]() {
       fence_proxy_async();
@@ -371,17 +387,17 @@ field_tc_kernel(const __grid_constant__ TcProgram prog, const FieldArgs args,
         row.x[c] = __ldg(args.origins + row.ray * 3 + c) + z * __ldg(args.directions + row.ray * 3 + c);
       const float* cond = args.cond + row.ray * prog.cond_stride;
       if (do_warp) {
-        if (args.fast_encode) posenc_fast_to_block(ins, r, row.x, prog.Fw, args.window, cond, prog.G);
-        else posenc_to_block(ins, r, row.x, prog.Fw, args.window, cond, prog.G);
+        if (args.fast_encode) posenc_fast_to_block(ins, r, row.x, prog.Fw, args.window, cond, prog.G, cb, ce);
+        else posenc_to_block(ins, r, row.x, prog.Fw, args.window, cond, prog.G, cb, ce);
       } else {
-        if (args.warped && row.valid) {
+        if (args.warped && row.valid && hs == 0) {
 #pragma unroll
           for (int c = 0; c < 3; ++c) args.warped[m * 3 + c] = row.x[c];
         }
-        if (args.fast_encode) posenc_fast_to_block(ins, r, row.x, prog.Fp, nullptr, nullptr, 0);
-        else posenc_to_block(ins, r, row.x, prog.Fp, nullptr, nullptr, 0);
+        if (args.fast_encode) posenc_fast_to_block(ins, r, row.x, prog.Fp, nullptr, nullptr, 0, cb, ce);
+        else posenc_to_block(ins, r, row.x, prog.Fp, nullptr, nullptr, 0, cb, ce);
       }
-      row.alpha = __ldg(aux + prog.alpha_b_off);
+      row.alpha = hs == 0 ? __ldg(aux + prog.alpha_b_off) : 0.f;
     };
 
     int pair = blockIdx.x;
@@ -392,57 +408,76 @@ field_tc_kernel(const __grid_constant__ TcProgram prog, const FieldArgs args,
     for (; pair < num_pairs; pair += gridDim.x) {
       for (int si = first_step; si <= last_step; ++si) {
         const TcStep& st = prog.steps[si];
-        // This step's biases: staged in shared memory by the 256 epilogue threads
+        // This step's biases: staged in shared memory by 256 epilogue threads
         // (value prefetched during the previous step), next step's prefetched now.
         float* bias = bias_s + (n_step & 1) * 256;
-        bias[tid] = next_bias;
-        {
+        if (tid < 256) {
+          bias[tid] = next_bias;
           int nsi = si + 1, npair = pair;
           if (nsi > last_step) { nsi = first_step; npair = pair + gridDim.x; }
           if (npair < num_pairs) next_bias = __ldg(aux + prog.steps[nsi].b_off + tid);
         }
         ++n_step;
-        asm volatile("bar.sync 1, 256;" ::: "memory");
+        epi_sync();
+        if (kH == 2 && merge_alpha) {
+          // the partner (columns' other half) left its alpha partial in the input block
+          if (hs == 0) row.alpha += reinterpret_cast<const float*>(ins)[r];
+          merge_alpha = false;
+          epi_sync();                                   // before anybody rewrites the input block
+        }
         if (st.epi == kEpiHidden) {
-          const int np = st.chunk_n / 32;              // 32-column pieces per chunk (2 or 4)
+          const int cols = st.chunk_n / kH;            // columns of a chunk handled by this thread
+          const int np = cols / 32;                    // 32-column pieces: 4, 2 or 1
+          const int cbase = hs * cols;
           const bool relu = st.relu != 0, adot = st.alpha_dot != 0;
           const __nv_bfloat16* aw = alpha_s;
           // ---- chunk 0: results are held in registers until the MMAs of chunk 1
           //      no longer read the blocks they overwrite ----
-          uint32_t packed[64];
+          uint32_t packed[64 / kH];
           mbar_wait(&bars->acc_ready[0], n_acc0++ & 1);
           tc_fence_after();
           tr.ev(si, 0);
-#pragma unroll
-          for (int pp = 0; pp < 2; ++pp) {
-            if (2 * pp < np && !(args.debug & 1)) {
-              float va[32], vb[32];
-              tmem_ld32(t_lane + (2 * pp) * 32, va);
-              tmem_ld32(t_lane + (2 * pp + 1) * 32, vb);
+          if (!(args.debug & 1)) {
+            if (kH == 2 && np == 1) {
+              float va[32];
+              tmem_ld32(t_lane + cbase, va);
               tmem_ld_wait();
-              epi_piece(va, bias + (2 * pp) * 32, relu, adot, aw + (2 * pp) * 32, row.alpha, packed + (2 * pp) * 16);
-              epi_piece(vb, bias + (2 * pp + 1) * 32, relu, adot, aw + (2 * pp + 1) * 32, row.alpha, packed + (2 * pp + 1) * 16);
+              epi_piece(va, bias + cbase, relu, adot, aw + cbase, row.alpha, packed);
+            } else {
+#pragma unroll
+              for (int pp = 0; pp < 2 / kH; ++pp) {
+                if (2 * pp < np) {
+                  float va[32], vb[32];
+                  const int col = cbase + 2 * pp * 32;
+                  tmem_ld32(t_lane + col, va);
+                  tmem_ld32(t_lane + col + 32, vb);
+                  tmem_ld_wait();
+                  epi_piece(va, bias + col, relu, adot, aw + col, row.alpha, packed + (2 * pp) * 16);
+                  epi_piece(vb, bias + col + 32, relu, adot, aw + col + 32, row.alpha, packed + (2 * pp + 1) * 16);
+                }
+              }
             }
           }
           tr.ev(si, 1);
           mbar_wait(&bars->x_free, n_free++ & 1);
           tr.ev(si, 2);
 #pragma unroll
-          for (int p = 0; p < 4; ++p) {
+          for (int p = 0; p < 4 / kH; ++p) {
             if (p < np && !(args.debug & 1)) {
-              uint8_t* blk = xs + (p >> 1) * kABlockBytes;
+              const int col = cbase + 32 * p;
+              uint8_t* blk = xs + (col >> 6) * kABlockBytes;
 #pragma unroll
               for (int q = 0; q < 4; ++q) {
                 uint4 o = make_uint4(packed[p * 16 + q * 4], packed[p * 16 + q * 4 + 1],
                                      packed[p * 16 + q * 4 + 2], packed[p * 16 + q * 4 + 3]);
-                *reinterpret_cast<uint4*>(blk + swz_off(r, (p & 1) * 4 + q)) = o;
+                *reinterpret_cast<uint4*>(blk + swz_off(r, ((col & 63) >> 3) + q)) = o;
               }
             }
           }
           // The input block is the first K-block of the next step (read right after
           // x_ready[0]); every earlier reader of it (the skip layer) is complete.
           if (st.write_cond)
-            cond_to_block(ins, r, args.cond + row.ray * prog.cond_stride + prog.G, prog.rc);
+            cond_to_block(ins, r, args.cond + row.ray * prog.cond_stride + prog.G, prog.rc, cb, ce);
           fence_proxy_async();
           tc_fence_before();
           mbar_arrive(&bars->x_ready[0]);
@@ -451,32 +486,48 @@ field_tc_kernel(const __grid_constant__ TcProgram prog, const FieldArgs args,
           mbar_wait(&bars->acc_ready[1], n_acc1++ & 1);
           tc_fence_after();
           tr.ev(si, 4);
+          if (!(args.debug & 1)) {
 #pragma unroll
-          for (int pp = 0; pp < 2; ++pp) {
-            if (2 * pp < np && !(args.debug & 1)) {
-              float va[32], vb[32];
-              const int col0 = st.chunk_n + 2 * pp * 32;
-              tmem_ld32(t_lane + col0, va);
-              tmem_ld32(t_lane + col0 + 32, vb);
-              tmem_ld_wait();
-              uint32_t pk[32];
-              epi_piece(va, bias + col0, relu, adot, aw + col0, row.alpha, pk);
-              epi_piece(vb, bias + col0 + 32, relu, adot, aw + col0 + 32, row.alpha, pk + 16);
-              // 64 columns = one K-block row (col0 is a multiple of 64)
-              uint8_t* blk = xs + (col0 >> 6) * kABlockBytes;
+            for (int pp = 0; pp < 2; ++pp) {
+              const bool two = (kH == 1) || np > 1;   // kH = 1: always pairs of pieces
+              if (pp * 2 < np || (kH == 2 && np == 1 && pp == 0)) {
+                float va[32], vb[32];
+                uint32_t pk[32];
+                const int col = st.chunk_n + cbase + 2 * pp * 32;
+                tmem_ld32(t_lane + col, va);
+                if (two) tmem_ld32(t_lane + col + 32, vb);
+                tmem_ld_wait();
+                epi_piece(va, bias + col, relu, adot, aw + col, row.alpha, pk);
+                if (two) epi_piece(vb, bias + col + 32, relu, adot, aw + col + 32, row.alpha, pk + 16);
 #pragma unroll
-              for (int q = 0; q < 8; ++q) {
-                uint4 o = make_uint4(pk[q * 4], pk[q * 4 + 1], pk[q * 4 + 2], pk[q * 4 + 3]);
-                *reinterpret_cast<uint4*>(blk + swz_off(r, q)) = o;
+                for (int h2 = 0; h2 < 2; ++h2) {
+                  if (h2 == 0 || two) {
+                    const int c2 = col + 32 * h2;
+                    uint8_t* blk = xs + (c2 >> 6) * kABlockBytes;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                      uint4 o = make_uint4(pk[h2 * 16 + q * 4], pk[h2 * 16 + q * 4 + 1],
+                                           pk[h2 * 16 + q * 4 + 2], pk[h2 * 16 + q * 4 + 3]);
+                      *reinterpret_cast<uint4*>(blk + swz_off(r, ((c2 & 63) >> 3) + q)) = o;
+                    }
+                  }
+                }
               }
             }
+          }
+          if (kH == 2 && adot) {
+            // hand the alpha partial of this half to the partner thread of the row
+            // through the (currently unused) input block; merged at the next step.
+            if (hs == 1) reinterpret_cast<float*>(ins)[r] = row.alpha;
+            merge_alpha = true;
           }
           fence_proxy_async();
           tc_fence_before();
           mbar_arrive(&bars->x_ready[1]);
           tr.ev(si, 5);
         } else {
-          // ---- heads: N = 16 accumulator columns, one chunk ----
+          // ---- heads: N = 16 accumulator columns, one chunk (both threads of a
+          //      row do the scalar work; they split the input-block chunks) ----
           float v[16];
           mbar_wait(&bars->acc_ready[0], n_acc0++ & 1);
           tc_fence_after();
@@ -495,7 +546,7 @@ field_tc_kernel(const __grid_constant__ TcProgram prog, const FieldArgs args,
             }
 #pragma unroll
             for (int c = 0; c < 3; ++c) row.x[c] = y[c];
-            if (args.warped && row.valid) {
+            if (args.warped && row.valid && hs == 0) {
 #pragma unroll
               for (int c = 0; c < 3; ++c) args.warped[row.m * 3 + c] = y[c];
             }
@@ -504,12 +555,12 @@ field_tc_kernel(const __grid_constant__ TcProgram prog, const FieldArgs args,
               const int nxt = pair + gridDim.x;
               if (nxt < num_pairs) begin_pair(nxt);
             } else {
-              if (args.fast_encode) posenc_fast_to_block(ins, r, row.x, prog.Fp, nullptr, nullptr, 0);
-              else posenc_to_block(ins, r, row.x, prog.Fp, nullptr, nullptr, 0);
+              if (args.fast_encode) posenc_fast_to_block(ins, r, row.x, prog.Fp, nullptr, nullptr, 0, cb, ce);
+              else posenc_to_block(ins, r, row.x, prog.Fp, nullptr, nullptr, 0, cb, ce);
             }
             arrive_both();
           } else {
-            if (row.valid && args.samples) {
+            if (row.valid && args.samples && hs == 0) {
               float4 o;
               o.x = sigmoidf(v[0]); o.y = sigmoidf(v[1]); o.z = sigmoidf(v[2]);
               o.w = apply_act(row.alpha, prog.sigma_act);
@@ -527,7 +578,7 @@ field_tc_kernel(const __grid_constant__ TcProgram prog, const FieldArgs args,
     tc_fence_before();
   }
   __syncthreads();
-  if (warp == 8) tmem_dealloc(tmem_base, 512);
+  if (warp == kMmaWarp) tmem_dealloc(tmem_base, 512);
 }
 
 // ---------------------------------------------------------------------------
@@ -706,7 +757,8 @@ inline int create_tc(nfb_handle* h) {
   if (cudaMalloc(&h->d_wpack, (size_t)wbytes) != cudaSuccess) return fail("cudaMalloc wpack failed");
   if (cudaMalloc(&h->d_aux, (size_t)auxf * sizeof(float)) != cudaSuccess) return fail("cudaMalloc aux failed");
   if (cudaMemset(h->d_aux, 0, (size_t)auxf * sizeof(float)) != cudaSuccess) return fail("cudaMemset failed");
-  if (cudaFuncSetAttribute(field_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes) != cudaSuccess)
+  if (cudaFuncSetAttribute(field_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes) != cudaSuccess ||
+      cudaFuncSetAttribute(field_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes) != cudaSuccess)
     return fail("cannot reserve %d bytes of shared memory for the tcgen05 kernel", kTcSmemBytes);
   return 0;
 }
@@ -763,7 +815,12 @@ inline int pack_tc(nfb_handle* h, cudaStream_t s) {
 inline int run_field_tc(nfb_handle* h, int level, const FieldArgs& a, cudaStream_t s) {
   const long long pairs = (a.num_rows + kPairRows - 1) / kPairRows;
   const int grid = (int)std::min<long long>(pairs, h->sm_count);
-  field_tc_kernel<<<grid, kTcThreads, kTcSmemBytes, s>>>(h->tcprog[level], a, h->d_wpack, h->d_aux, (int)pairs);
+  // NFB_TC_EPI_WARPS=8|16 selects the epilogue width (default: see kDefaultEpiWarps).
+  static const int epi_warps = getenv("NFB_TC_EPI_WARPS") ? atoi(getenv("NFB_TC_EPI_WARPS")) : kDefaultEpiWarps;
+  if (epi_warps == 16)
+    field_tc_kernel<2><<<grid, kTcThreads16, kTcSmemBytes, s>>>(h->tcprog[level], a, h->d_wpack, h->d_aux, (int)pairs);
+  else
+    field_tc_kernel<1><<<grid, kTcThreads, kTcSmemBytes, s>>>(h->tcprog[level], a, h->d_wpack, h->d_aux, (int)pairs);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail("field_tc_kernel launch failed: %s", cudaGetErrorString(e));
   h->launches++;

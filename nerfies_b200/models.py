@@ -50,7 +50,8 @@ def _prep_ids(t, device):
     return None
   t = torch.as_tensor(t)
   if t.dim() > 1:
-    t = t.reshape(t.shape[0], -1)[:, 0]
+    # (B,1) -> (B); an empty batch cannot be reshaped with -1.
+    t = t.reshape(t.shape[0], -1)[:, 0] if t.numel() else t.reshape(0)
   # torch has no first-class uint32 arithmetic: carry the bits in int32.
   return t.to(device=device, dtype=torch.int32).contiguous()
 

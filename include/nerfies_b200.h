@@ -155,7 +155,8 @@ float nfb_field_time_ms(nfb_handle* h, int level);
 
 /* Debug aid: block 0 of the tensor-core field kernel appends (tag, clock64)
  * pairs to `buffer` (device, 1 + 2*capacity int64; buffer[0] = record count,
- * zero it first).  NULL disables tracing. */
+ * zero it first).  NULL disables tracing.  Only builds compiled with -DNFB_TRACE
+ * carry the tracer; others return -1 for a non-NULL buffer. */
 int nfb_set_trace(nfb_handle* h, long long* buffer, int capacity);
 
 /* Hardware self-test of the tcgen05 building blocks (UMMA descriptors, 128-byte

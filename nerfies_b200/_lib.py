@@ -7,7 +7,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libnerfies_b200.so')
+# NFB_LIB_PATH: developer override used to A/B kernel build variants (tools/build_variant.py).
+LIB_PATH = os.environ.get('NFB_LIB_PATH') or os.path.join(_HERE, 'libnerfies_b200.so')
 
 # Every symbol include/nerfies_b200.h declares (checked by tests/test_abi.py).
 SYMBOLS = [

@@ -46,7 +46,9 @@ struct FieldArgs {
   int use_warp;              // run the warp net
   int warp_only;             // stop after the warp (nfb_warp_forward)
   int fast_encode;           // bf16 mode: octave-recurrence positional encoding
-  int debug;                 // NFB_DEBUG bits: 1 = epilogue skips TMEM loads/math/stores (timing experiments)
+  int debug;                 // NFB_DEBUG bits (timing experiments, results are garbage): 1 = hidden-layer epilogues skip
+                             // TMEM loads, math and stores; 2 / 4 (-DNFB_EPI_DEBUG builds) = skip only the activation stores / only loads + math;
+                             // 8 = the MMA issuer first waits on a barrier that never completes (abort-path test)
   long long* trace;          // debug: (tag, clock) records of block 0, or nullptr
   int trace_cap;
 };

@@ -362,8 +362,40 @@ int run_resample(nfb_handle* h, int B, const float* zc, const float* wc, const f
   return launch_check(h, "resample_kernel");
 }
 
+// The tcgen05 kernels never trap on a protocol error (see tc_common.cuh,
+// mbar_wait): they raise a flag in mapped pinned host memory instead.  One int per
+// process; every device's copy of the g_nfb_abort symbol points at it.
+int* g_abort_host = nullptr;
+unsigned long long g_abort_devices = 0;   // devices whose symbol has been set
+
+int ensure_abort_flag() {
+#ifdef NFB_WITH_TC
+  int dev = 0;
+  NFB_CUDA(cudaGetDevice(&dev));
+  if (!g_abort_host) {
+    NFB_CUDA(cudaHostAlloc(&g_abort_host, sizeof(int), cudaHostAllocMapped | cudaHostAllocPortable));
+    *g_abort_host = 0;
+  }
+  if (dev < 64 && !(g_abort_devices >> dev & 1)) {
+    int* dptr = nullptr;
+    NFB_CUDA(cudaHostGetDevicePointer(&dptr, g_abort_host, 0));
+    NFB_CUDA(cudaMemcpyToSymbol(nfb::tc::g_nfb_abort, &dptr, sizeof(dptr)));
+    g_abort_devices |= 1ull << dev;
+  }
+#endif
+  return 0;
+}
+
+int abort_check() {
+  if (g_abort_host && *reinterpret_cast<volatile int*>(g_abort_host))
+    return fail("a tcgen05 kernel aborted: an mbarrier wait timed out (protocol error); its results are invalid "
+                "and this process cannot run further tensor-core launches");
+  return 0;
+}
+
 int check_call(nfb_handle* h, int B) {
   if (!h) return fail("null handle");
+  if (abort_check()) return -1;
   if (!h->params_set) return fail("nfb_set_params has not been called");
   if (B < 0 || B > h->max_rays) return fail("num_rays=%d outside [0, max_rays=%d]", B, h->max_rays);
   return 0;
@@ -379,6 +411,9 @@ long long nfb_kernel_launches(const nfb_handle* h) { return h ? h->launches : 0;
 
 int nfb_set_trace(nfb_handle* h, long long* buffer, int capacity) {
   if (!h) return fail("null handle");
+#ifndef NFB_TRACE
+  if (buffer) return fail("this build carries no tracer; rebuild with -DNFB_TRACE (tools/build_variant.py)");
+#endif
   h->trace = buffer; h->trace_cap = buffer ? capacity : 0;
   return 0;
 }
@@ -408,6 +443,7 @@ float nfb_field_time_ms(nfb_handle* h, int level) {
 int nfb_selftest_gemm(int K, int N, const float* A, const float* W, float* C, void* stream) {
   using namespace nfb::tc;
   if (K < 1 || K > kSelfMaxKb * kBlockK || N < 1 || N > 256) return fail("selftest: K<=320, N<=256");
+  if (ensure_abort_flag() || abort_check()) return -1;
   cudaStream_t s = (cudaStream_t)stream;
   const int nkb = (K + kBlockK - 1) / kBlockK;
   const int n_rows = (N + 15) / 16 * 16;
@@ -427,12 +463,13 @@ int nfb_selftest_gemm(int K, int N, const float* A, const float* W, float* C, vo
   cudaFree(d_map);
   cudaFree(d_w);
   if (e != cudaSuccess) return fail("selftest kernel failed: %s", cudaGetErrorString(e));
-  return 0;
+  return abort_check();
 }
 
 int nfb_selftest_microbench(int mode, int n, int reps, int nwarps, long long* out) {
   using namespace nfb::tc;
   if (!out || n < 16 || n > 256 || n % 16) return fail("microbench: bad arguments");
+  if (ensure_abort_flag() || abort_check()) return -1;
   long long* d = nullptr;
   unsigned char* g = nullptr;
   NFB_CUDA(cudaMalloc(&d, 4 * sizeof(long long)));
@@ -450,7 +487,7 @@ int nfb_selftest_microbench(int mode, int n, int reps, int nwarps, long long* ou
   if (e == cudaSuccess) e = cudaMemcpy(out, d, 3 * sizeof(long long), cudaMemcpyDeviceToHost);
   cudaFree(d);
   if (e != cudaSuccess) return fail("microbench failed: %s", cudaGetErrorString(e));
-  return 0;
+  return abort_check();
 }
 
 int nfb_create(const nfb_config* cfg, int max_rays, nfb_handle** out) {
@@ -473,6 +510,7 @@ int nfb_create(const nfb_config* cfg, int max_rays, nfb_handle** out) {
   if (cudaGetDeviceProperties(&prop, h->device) != cudaSuccess) return bail(fail("cudaGetDeviceProperties failed"));
   if (prop.major != 10) return bail(fail("device is sm_%d%d; this library is built for sm_100a only", prop.major, prop.minor));
   h->sm_count = prop.multiProcessorCount;
+  if (ensure_abort_flag()) return bail(-1);
   if (build_programs(h)) return bail(-1);
   if (build_tables(h)) return bail(-1);
   const nfb_config& c = h->cfg;
@@ -675,6 +713,7 @@ int nfb_render_forward_host(nfb_handle* h, int B, const float* origins, const fl
   if (out_fine && fine)
     NFB_CUDA(cudaMemcpyAsync(h->h_out + mr * 6, h->d_out_f, (size_t)B * 6 * sizeof(float), cudaMemcpyDeviceToHost, s));
   NFB_CUDA(cudaStreamSynchronize(s));
+  if (abort_check()) return -1;
   if (out_coarse) memcpy(out_coarse, h->h_out, (size_t)B * 6 * sizeof(float));
   if (out_fine && fine) memcpy(out_fine, h->h_out + mr * 6, (size_t)B * 6 * sizeof(float));
   return 0;

@@ -90,6 +90,7 @@ struct nfb_handle {
   int trace_cap = 0;
   // tensor-core path (precision != fp32)
   nfb::tc::TcProgram tcprog[2];
+  nfb::tc::TcBias tcbias[2];          // host copy of the per-step biases (kernel parameter)
   unsigned char* d_wpack = nullptr;   // bf16 weight units, shared-memory image
   float* d_aux = nullptr;             // fp32 biases + alpha head
   long long wpack_bytes = 0, aux_floats = 0;

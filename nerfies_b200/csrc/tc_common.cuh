@@ -60,26 +60,81 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
                "r"(bytes)
                : "memory");
 }
+// Host-visible abort flag: a mapped pinned int (one per process, set up by
+// ensure_abort_flag() in nfb_api.cu).  Nonzero = some mbarrier wait timed out.
+__device__ int* g_nfb_abort = nullptr;
+
 // Waits for the completion of the phase with the given parity.  A wait that
-// spins "forever" traps instead of hanging the GPU (a protocol bug, not a
-// condition that can occur in a correct run).
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+// spins "forever" (a protocol bug, not a condition that can occur in a correct
+// run) does not hang the GPU: after 2^22 probes (tens of milliseconds at least; a
+// legitimate wait is over within microseconds) the thread raises the host-visible
+// abort flag, marks itself `dead` and returns; a dead thread returns from every
+// later wait at once.  All roles of a CTA wait concurrently, so their time-outs
+// expire together and the kernel drains; the host API then reports the error.
+// Deliberately no __trap()/printf here: trap exits inside the epilogue keep ptxas
+// from allocating the registers that setmaxnreg.inc hands to those warpgroups, and
+// the spin loop is four PTX instructions (it sits on every hand-off's critical path).
+template <bool kBusyPoll>
+__device__ __forceinline__ void mbar_wait_impl(uint64_t* bar, uint32_t parity, uint32_t& dead) {
+  if (dead) return;
   const uint32_t addr = smem_u32(bar);
-  uint32_t done = 0;
-  for (uint32_t spin = 0; !done; ++spin) {
+  uint32_t done;
+  constexpr uint32_t kWaitProbes = 1u << 22;
+  if (kBusyPoll) {
+    // test_wait never suspends the thread: lowest wake-up latency, burns issue slots.
     asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
+        "{\n\t.reg .pred p;\n\t.reg .u32 n;\n\t"
+        "mov.u32 n, 0;\n"
+        "NFB_W: mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "@p bra NFB_D;\n\t"
+        "add.u32 n, n, 1;\n\t"
+        "setp.ne.u32 p, n, %3;\n\t"
+        "@p bra NFB_W;\n\t"
+        "setp.eq.u32 p, n, 0;\n"
+        "NFB_D: selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(done)
-        : "r"(addr), "r"(parity)
+        : "r"(addr), "r"(parity), "r"(kWaitProbes * 16)
         : "memory");
-    if (!done && spin > (1u << 26)) {
-      printf("nfb: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", blockIdx.x,
-             threadIdx.x, addr, parity);
-      __trap();
-    }
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .u32 n;\n\t"
+        "mov.u32 n, 0;\n"
+        "NFB_W: mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "@p bra NFB_D;\n\t"
+        "add.u32 n, n, 1;\n\t"
+        "setp.ne.u32 p, n, %3;\n\t"
+        "@p bra NFB_W;\n\t"
+        "setp.eq.u32 p, n, 0;\n"
+        "NFB_D: selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity), "r"(kWaitProbes)
+        : "memory");
   }
+  if (!done) {                       // time-out: raise the abort flag, give up for good
+    volatile int* ab = g_nfb_abort;
+    if (ab) *ab = 1;
+    dead = 1;
+  }
+}
+#ifdef NFB_WAIT_TEST
+constexpr bool kEpiBusyPoll = true;
+#else
+constexpr bool kEpiBusyPoll = false;
+#endif
+#if defined(NFB_WAIT_TEST) || defined(NFB_WAIT_TEST_ISSUER)
+constexpr bool kIssuerBusyPoll = true;
+#else
+constexpr bool kIssuerBusyPoll = false;
+#endif
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, uint32_t& dead) {
+  mbar_wait_impl<kEpiBusyPoll>(bar, parity, dead);
+}
+__device__ __forceinline__ void mbar_wait_issuer(uint64_t* bar, uint32_t parity, uint32_t& dead) {
+  mbar_wait_impl<kIssuerBusyPoll>(bar, parity, dead);
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t dead = 0;
+  mbar_wait(bar, parity, dead);
 }
 
 // Non-blocking probe of a phase (true = complete).
@@ -287,28 +342,31 @@ __device__ __forceinline__ uint32_t issue_half1(uint32_t d1, uint64_t ad1, uint6
                                                 uint32_t accumulate, uint32_t bar_empty,
                                                 uint32_t bar_xfree, uint32_t bar_acc, uint32_t probe_w,
                                                 uint32_t par_w, uint32_t probe_x0, uint32_t probe_x1,
-                                                uint32_t par_x) {
+                                                uint32_t probe_x2, uint32_t par_x) {
   uint32_t out;
   asm volatile(
       "{\n\t"
-      ".reg .pred pacc, pt, pw, px0, px1, pd0, pd1, pcx, pca;\n\t"
+      ".reg .pred pacc, pt, pw, px0, px1, px2, pd0, pd1, pd2, pcx, pca;\n\t"
       ".reg .b64 a1, a2, a3, b1, b2, b3;\n\t"
-      ".reg .b32 t0, t1;\n\t"
+      ".reg .b32 t0, t1, t2;\n\t"
       "setp.ne.b32 pacc, %5, 0;\n\t"
       "setp.eq.b32 pt, 0, 0;\n\t"
       "setp.ne.b32 pd0, %11, 0;\n\t"
       "setp.ne.b32 pd1, %12, 0;\n\t"
+      "setp.ne.b32 pd2, %13, 0;\n\t"
       "setp.ne.b32 pcx, %7, 0;\n\t"
       "setp.ne.b32 pca, %8, 0;\n\t"
       "setp.eq.b32 px0, 1, 0;\n\t"
       "setp.eq.b32 px1, 1, 0;\n\t"
+      "setp.eq.b32 px2, 1, 0;\n\t"
       "add.u64 a1, %2, 2;\n\t add.u64 a2, %2, 4;\n\t add.u64 a3, %2, 6;\n\t"
       "add.u64 b1, %3, 2;\n\t add.u64 b2, %3, 4;\n\t add.u64 b3, %3, 6;\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%1], %2, %3, %4, pacc;\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%1], a1, b1, %4, pt;\n\t"
       "mbarrier.test_wait.parity.shared::cta.b64 pw, [%9], %10;\n\t"
-      "@pd0 mbarrier.test_wait.parity.shared::cta.b64 px0, [%11], %13;\n\t"
-      "@pd1 mbarrier.test_wait.parity.shared::cta.b64 px1, [%12], %13;\n\t"
+      "@pd0 mbarrier.test_wait.parity.shared::cta.b64 px0, [%11], %14;\n\t"
+      "@pd1 mbarrier.test_wait.parity.shared::cta.b64 px1, [%12], %14;\n\t"
+      "@pd2 mbarrier.test_wait.parity.shared::cta.b64 px2, [%13], %14;\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%1], a2, b2, %4, pt;\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%1], a3, b3, %4, pt;\n\t"
       "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%6];\n\t"
@@ -317,12 +375,15 @@ __device__ __forceinline__ uint32_t issue_half1(uint32_t d1, uint64_t ad1, uint6
       "selp.u32 %0, 1, 0, pw;\n\t"
       "selp.u32 t0, 2, 0, px0;\n\t"
       "selp.u32 t1, 4, 0, px1;\n\t"
+      "selp.u32 t2, 8, 0, px2;\n\t"
       "or.b32 %0, %0, t0;\n\t"
       "or.b32 %0, %0, t1;\n\t"
+      "or.b32 %0, %0, t2;\n\t"
       "}"
       : "=r"(out)
       : "r"(d1), "l"(ad1), "l"(bd), "r"(idesc), "r"(accumulate), "r"(bar_empty), "r"(bar_xfree),
-        "r"(bar_acc), "r"(probe_w), "r"(par_w), "r"(probe_x0), "r"(probe_x1), "r"(par_x)
+        "r"(bar_acc), "r"(probe_w), "r"(par_w), "r"(probe_x0), "r"(probe_x1), "r"(probe_x2),
+        "r"(par_x)
       : "memory");
   return out;
 }
@@ -340,6 +401,23 @@ __device__ __forceinline__ void store_chunk(uint8_t* block, int row, int chunk, 
   q.z = pack_bf16x2(v[4], v[5]);
   q.w = pack_bf16x2(v[6], v[7]);
   *reinterpret_cast<uint4*>(block + swz_off(row, chunk)) = q;
+}
+
+// Stores one 32-column piece (16 packed bf16 pairs) of a row into the activation
+// blocks.  `a0` = shared address of the row's chunk 0 in block 0 with the row's
+// swizzle term folded in (base + row*128 + ((row&7)<<4)); chunk c of the row is at
+// a0 ^ (c<<4).  The xor is a volatile asm so that ptxas recomputes the address (one
+// LOP3) instead of keeping 16 loop-invariant addresses alive across the layer loop.
+__device__ __forceinline__ void sts_piece(uint32_t a0, int col, const uint32_t* pk16) {
+  const uint32_t base = a0 + (uint32_t)(col >> 6) * 16384u;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    uint32_t addr;
+    asm volatile("xor.b32 %0, %1, %2;" : "=r"(addr) : "r"(base), "r"((uint32_t)((((col & 63) >> 3) + q) << 4)));
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk16[q * 4]),
+                 "r"(pk16[q * 4 + 1]), "r"(pk16[q * 4 + 2]), "r"(pk16[q * 4 + 3])
+                 : "memory");
+  }
 }
 
 // Weight packing (global memory image of the shared-memory operand): the

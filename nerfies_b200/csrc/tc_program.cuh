@@ -35,6 +35,7 @@ enum UnitFlags {
   kUCommitAcc1 = 16,    // commit acc_ready[1] after this unit
   kUCommitXFree = 32,   // commit x_free after this unit
   kUStepEnd = 64,       // last unit of its step
+  kUWaitX2 = 128,       // wait x_ready[2] (second half of the previous chunk-1 epilogue)
 };
 // Everything the issuer needs is precomputed on the host so that the single
 // issuing thread executes as few (serially dependent) instructions as possible
@@ -44,8 +45,8 @@ struct TcUnit {
   uint32_t dcol;           // accumulator column offset (sub-tile 0; sub-tile 1 = +256)
   uint32_t idesc;          // tcgen05 instruction descriptor (M=128, N=chunk)
   uint32_t flags;          // UnitFlags of this unit
-  uint32_t need;           // look-ahead bits that must be set before issuing: 1 weights | 2 x_ready[0] | 4 x_ready[1]
-  uint32_t probe_next;     // which x_ready barriers the NEXT unit (cyclically) needs: 2 | 4
+  uint32_t need;           // look-ahead bits that must be set before issuing: 1 weights | 2/4/8 x_ready[0/1/2]
+  uint32_t probe_next;     // which x_ready barriers the NEXT unit (cyclically) needs: 2 | 4 | 8
   uint32_t step;
 };
 
@@ -58,6 +59,13 @@ struct TcProgram {
   int warp_type, Fw, G, Fp, rc, cond_stride, sigma_act;
   int alpha_w_off, alpha_b_off;   // aux float offsets
   uint32_t units_per_pair;        // weight units streamed per tile pair
+};
+
+// Per-step biases (256 floats each), passed as a __grid_constant__ kernel
+// parameter: the epilogue reads them from the constant bank through the uniform
+// datapath instead of through the shared-memory pipe the MMAs are fed from.
+struct alignas(16) TcBias {
+  float4 b4[kMaxTcSteps * 64];
 };
 
 }  // namespace tc

@@ -135,3 +135,36 @@ def test_coarse_only_model_and_fullhd_dims_bf16():
   ref = O.render_forward(p, spec, rays, warp_alpha=8.0)
   mse = float(((out['fine']['rgb'].cpu() - ref['fine']['rgb'])**2).mean())
   assert -10 * np.log10(max(mse, 1e-20)) > 35
+
+
+def test_protocol_error_aborts_instead_of_hanging():
+  """NFB_DEBUG=8 makes the MMA issuer wait on an mbarrier that never completes.
+
+  The kernel must drain (bounded spin -> host-visible abort flag -> every other
+  waiter bails out) and the API must report the error, not hang the GPU."""
+  import subprocess, sys, os, textwrap
+  code = textwrap.dedent('''
+      import torch, nerfies_b200 as nb
+      cfg = nb.configs.ModelConfig(use_stratified_sampling=False, use_warp=True, warp_field_type='se3',
+                                   use_appearance_metadata=True, num_coarse_samples=32, num_fine_samples=32,
+                                   num_nerf_point_freqs=8, sigma_activation='softplus')
+      model, params = nb.construct_nerf(0, cfg, 256, range(10), [0], range(10), near=0.02, far=0.83,
+                                        precision='bf16', device='cuda:0')
+      g = torch.Generator().manual_seed(0)
+      rays = {'origins': torch.randn(256, 3, generator=g).cuda() * 0.1,
+              'directions': torch.nn.functional.normalize(torch.randn(256, 3, generator=g), dim=-1).cuda(),
+              'metadata': {'warp': torch.zeros(256, 1, dtype=torch.int32).cuda(),
+                           'appearance': torch.zeros(256, 1, dtype=torch.int32).cuda()}}
+      try:
+        model.apply({'params': params}, rays, warp_extra={'alpha': 8.0})
+        torch.cuda.synchronize()
+        model.apply({'params': params}, rays, warp_extra={'alpha': 8.0})
+        print('NO-ERROR')
+      except Exception as e:
+        print('ERROR:', e)
+  ''')
+  env = dict(os.environ, NFB_DEBUG='8')
+  root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+  out = subprocess.run([sys.executable, '-c', code], cwd=root, env=env, capture_output=True, text=True,
+                       timeout=120)
+  assert 'ERROR:' in out.stdout and 'mbarrier wait timed out' in out.stdout, (out.stdout, out.stderr[-2000:])

@@ -1,6 +1,11 @@
-"""Timeline of the tensor-core field kernel's block 0 (GPU box)."""
+"""Timeline of the tensor-core field kernel's block 0 (GPU box).
+
+Needs the tracer build:  python tools/build_variant.py trace -DNFB_TRACE
+"""
 import ctypes, os, sys
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+os.environ.setdefault('NFB_LIB_PATH', os.path.join(ROOT, 'nerfies_b200', '_variants', 'libnfb_trace.so'))
 import torch
 import bench
 import nerfies_b200 as nb
@@ -14,7 +19,8 @@ torch.cuda.synchronize()
 hd = model.handle(B)
 cap = 20000
 buf = torch.zeros(4 + 2 * cap, dtype=torch.int64, device='cuda')
-hd.lib.nfb_set_trace(hd.h, ctypes.c_void_p(buf.data_ptr()), cap)
+_lib_check = hd.lib.nfb_set_trace(hd.h, ctypes.c_void_p(buf.data_ptr()), cap)
+assert _lib_check == 0, 'tracer build missing: python tools/build_variant.py trace -DNFB_TRACE'
 from nerfies_b200 import _lib
 from nerfies_b200.models import _ptr, _stream
 z = torch.empty(B, 128, device='cuda')

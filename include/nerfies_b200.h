@@ -17,6 +17,11 @@
  *    stream has passed the call; the library owns only its workspace, allocated
  *    in nfb_create; nothing is allocated on the hot path;
  *  - return value 0 = success, < 0 = error (message via nfb_last_error());
+ *  - the tensor-core kernels never hang or trap on an internal protocol error:
+ *    a bounded mbarrier wait raises a process-wide abort flag (mapped host
+ *    memory), the kernel drains, and the _host entry point / every later call
+ *    returns an error ("a tcgen05 kernel aborted ..."); results of that launch
+ *    are invalid;
  *  - a handle is not thread-safe: one handle per GPU per process/rank.
  */
 #ifndef NERFIES_B200_H_

@@ -174,9 +174,15 @@ __device__ __forceinline__ void posenc_fast_to_block(uint8_t* block, int r, cons
     if (c >= c_begin && c < c_end) store_chunk(block, r, c, feat + c * 8);
 }
 
-// One 32-column piece of a hidden layer's epilogue: + bias, (alpha head dot),
-// round to bf16, ReLU on the packed pairs (rounding is monotone and keeps zero,
-// so relu-then-round == round-then-relu).
+// One 32-column piece of a hidden layer's epilogue: + bias (packed add.f32x2),
+// (alpha head dot), round to bf16 with the ReLU folded into the conversion
+// (cvt.rn.relu.bf16x2.f32; rounding is monotone and keeps zero, so
+// relu-then-round == round-then-relu).
+__device__ __forceinline__ uint64_t pack_f32x2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
 __device__ __forceinline__ void epi_piece(const float* v, const float4* __restrict__ bq4,
                                           bool relu, bool adot,
                                           const __nv_bfloat16* __restrict__ alpha_w32, float& alpha,
@@ -185,7 +191,15 @@ __device__ __forceinline__ void epi_piece(const float* v, const float4* __restri
 #pragma unroll
   for (int j = 0; j < 32; j += 4) {
     const float4 bq = bq4[j >> 2];                             // constant bank, warp-uniform address
+#ifdef NFB_NO_F32X2
     t[j] = v[j] + bq.x; t[j + 1] = v[j + 1] + bq.y; t[j + 2] = v[j + 2] + bq.z; t[j + 3] = v[j + 3] + bq.w;
+#else
+    uint64_t r0, r1;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r0) : "l"(pack_f32x2(v[j], v[j + 1])), "l"(pack_f32x2(bq.x, bq.y)));
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r1) : "l"(pack_f32x2(v[j + 2], v[j + 3])), "l"(pack_f32x2(bq.z, bq.w)));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(t[j]), "=f"(t[j + 1]) : "l"(r0));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(t[j + 2]), "=f"(t[j + 3]) : "l"(r1));
+#endif
   }
   if (adot) {
 #pragma unroll
@@ -201,12 +215,14 @@ __device__ __forceinline__ void epi_piece(const float* v, const float4* __restri
       }
     }
   }
-  const __nv_bfloat162 zero = __float2bfloat162_rn(0.f);
+  if (relu) {
 #pragma unroll
-  for (int j = 0; j < 16; ++j) {
-    __nv_bfloat162 pk = __floats2bfloat162_rn(t[2 * j], t[2 * j + 1]);
-    if (relu) pk = __hmax2(pk, zero);
-    out16[j] = *reinterpret_cast<uint32_t*>(&pk);
+    for (int j = 0; j < 16; ++j)
+      asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(out16[j]) : "f"(t[2 * j + 1]), "f"(t[2 * j]));
+  } else {
+#pragma unroll
+    for (int j = 0; j < 16; ++j)
+      asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(out16[j]) : "f"(t[2 * j + 1]), "f"(t[2 * j]));
   }
 }
 

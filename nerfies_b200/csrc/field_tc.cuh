@@ -10,12 +10,15 @@
 //               cp.async.bulk through a 4-stage mbarrier ring, each unit used by
 //               both sub-tiles (256 rows per weight byte fetched);
 //   D         = fp32 accumulators in TMEM (2 sub-tiles x 256 columns).
-// Warp roles: warps 0-7 epilogue (one thread per row: tcgen05.ld -> bias ->
-// activation -> bf16 -> swizzled st.shared; also the SE(3) exp-map, the
-// positional encodings and the final sigmoid/softplus), warp 8 lane 0 issues the
-// MMAs, warp 9 lane 0 the weight copies.  The N dimension of a layer is issued
-// in two chunks so that the epilogue of chunk 0 overlaps the MMAs of chunk 1
-// and the next layer's first K-blocks overlap the epilogue of chunk 1.
+// Warp roles (3 warpgroups, 384 threads): warps 0-7 epilogue (one thread per row:
+// tcgen05.ld -> add.f32x2 bias from the constant bank -> cvt.relu.bf16x2 ->
+// swizzled st.shared; also the SE(3) exp-map, the positional encodings and the
+// final sigmoid/softplus), warp 8 lane 0 issues the MMAs, warp 9 lane 0 the weight
+// copies, warps 10-11 only complete the control warpgroup.  setmaxnreg gives the
+// epilogue warpgroups 232 registers per thread and leaves the control group 40.
+// The N dimension of a layer is issued in two chunks so that the epilogue of
+// chunk 0 overlaps the MMAs of chunk 1 and the next layer's first K-blocks
+// overlap the epilogue of chunk 1.
 // Activations never leave the SM; per sample 16 B (r,g,b,sigma) go to HBM.
 #pragma once
 #include "field_simt.cuh"   // FieldArgs

@@ -158,6 +158,33 @@ int nfb_warp_forward(nfb_handle* h, int num_points, const float* points,
 int nfb_set_profiling(nfb_handle* h, int enabled);
 float nfb_field_time_ms(nfb_handle* h, int level);
 
+/* ---- camera -> rays ------------------------------------
+ * Mirrors the fields of nerfies.camera.Camera (camera.py:110-137). */
+typedef struct nfb_camera {
+  float orientation[9];           /* world-to-camera rotation, row-major        */
+  float position[3];
+  float focal_length;
+  float principal_point[2];
+  float skew;
+  float pixel_aspect_ratio;
+  float radial_distortion[3];     /* k1 k2 k3                                   */
+  float tangential_distortion[2]; /* p1 p2                                      */
+  int image_size[2];              /* (width, height)                            */
+} nfb_camera;
+
+/* Replaces datasets/core.py:50-75 camera_to_rays (camera.py:317-321 pixel centres
+ * + camera.py:244-269 pixels_to_rays) for the pixels [first_pixel,
+ * first_pixel + count) of the frame in row-major order: origins (count,3) =
+ * camera position, directions (count,3) unit, pixels (count,2) centres.
+ * origins and pixels may be NULL.  Needs no handle. */
+int nfb_camera_rays(const nfb_camera* cam, long long first_pixel, long long count,
+                    float* origins, float* directions, float* pixels, void* stream);
+
+/* Replaces Camera.pixels_to_rays (camera.py:244-269) for arbitrary float32 pixel
+ * positions (n,2) -> unit world-space directions (n,3). */
+int nfb_pixels_to_rays(const nfb_camera* cam, const float* pixels, long long n,
+                       float* directions, void* stream);
+
 /* Debug aid: block 0 of the tensor-core field kernel appends (tag, clock64)
  * pairs to `buffer` (device, 1 + 2*capacity int64; buffer[0] = record count,
  * zero it first).  NULL disables tracing.  Only builds compiled with -DNFB_TRACE

@@ -17,6 +17,7 @@ SYMBOLS = [
     'nfb_render_samples', 'nfb_sample_pdf', 'nfb_coarse_z_vals',
     'nfb_warp_forward', 'nfb_kernel_launches', 'nfb_last_error', 'nfb_version',
     'nfb_set_profiling', 'nfb_field_time_ms', 'nfb_selftest_gemm', 'nfb_set_trace', 'nfb_selftest_microbench',
+    'nfb_camera_rays', 'nfb_pixels_to_rays',
 ]
 
 ACTIVATIONS = {'none': 0, 'relu': 1, 'elu': 2, 'leaky_relu': 3, 'tanh': 4,
@@ -66,6 +67,21 @@ class NfbConfig(ctypes.Structure):
       ('near_plane', ctypes.c_float),
       ('far_plane', ctypes.c_float),
       ('precision', ctypes.c_int),
+  ]
+
+
+class NfbCamera(ctypes.Structure):
+  """struct nfb_camera - field order must match the header."""
+  _fields_ = [
+      ('orientation', ctypes.c_float * 9),
+      ('position', ctypes.c_float * 3),
+      ('focal_length', ctypes.c_float),
+      ('principal_point', ctypes.c_float * 2),
+      ('skew', ctypes.c_float),
+      ('pixel_aspect_ratio', ctypes.c_float),
+      ('radial_distortion', ctypes.c_float * 3),
+      ('tangential_distortion', ctypes.c_float * 2),
+      ('image_size', ctypes.c_int * 2),
   ]
 
 
@@ -128,6 +144,11 @@ def load():
   lib.nfb_set_trace.restype = ci
   lib.nfb_selftest_microbench.argtypes = [ci, ci, ci, ci, vp]
   lib.nfb_selftest_microbench.restype = ci
+  ll = ctypes.c_longlong
+  lib.nfb_camera_rays.argtypes = [ctypes.POINTER(NfbCamera), ll, ll, vp, vp, vp, vp]
+  lib.nfb_camera_rays.restype = ci
+  lib.nfb_pixels_to_rays.argtypes = [ctypes.POINTER(NfbCamera), vp, ll, vp, vp]
+  lib.nfb_pixels_to_rays.restype = ci
   lib.nfb_last_error.argtypes = []
   lib.nfb_last_error.restype = ctypes.c_char_p
   lib.nfb_version.argtypes = []

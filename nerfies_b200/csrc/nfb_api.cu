@@ -15,6 +15,7 @@
 #include "nfb_handle.h"
 #include "field_simt.cuh"
 #include "ray_kernels.cuh"
+#include "camera_kernels.cuh"
 #include "tc_common.cuh"
 #include "tc_selftest.cuh"
 #ifdef NFB_WITH_TC
@@ -408,6 +409,42 @@ extern "C" {
 const char* nfb_last_error(void) { return g_error.c_str(); }
 const char* nfb_version(void) { return "nerfies_b200 0.1 sm_100a"; }
 long long nfb_kernel_launches(const nfb_handle* h) { return h ? h->launches : 0; }
+
+static int launch_camera(const nfb_camera* cam, const float* pixels_in, long long first, long long count,
+                         float* origins, float* directions, float* pixels_out, void* stream) {
+  if (!cam || !directions) return fail("null argument");
+  if (count < 0 || first < 0) return fail("negative pixel range");
+  if (cam->image_size[0] < 1 || cam->image_size[1] < 1) return fail("image_size must be positive");
+  if (!pixels_in && first + count > (long long)cam->image_size[0] * cam->image_size[1])
+    return fail("pixel range [%lld, %lld) exceeds the %d x %d frame", first, first + count,
+                cam->image_size[0], cam->image_size[1]);
+  if (!(cam->focal_length != 0.f) || !(cam->pixel_aspect_ratio != 0.f)) return fail("focal_length and pixel_aspect_ratio must be non-zero");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail("no CUDA device: nerfies_b200 has no CPU path");
+  if (count == 0) return 0;
+  nfb::CameraArgs a{};
+  a.cam = *cam; a.pixels_in = pixels_in; a.first = first; a.count = count;
+  a.origins = origins; a.directions = directions; a.pixels_out = pixels_out;
+  a.has_distortion = 0;                                   // camera.py:201-207
+  for (int i = 0; i < 3; ++i) a.has_distortion |= cam->radial_distortion[i] != 0.f;
+  for (int i = 0; i < 2; ++i) a.has_distortion |= cam->tangential_distortion[i] != 0.f;
+  nfb::camera_rays_kernel<<<(unsigned)((count + 255) / 256), 256, 0, (cudaStream_t)stream>>>(a);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail("camera_rays_kernel launch failed: %s", cudaGetErrorString(e));
+  return 0;
+}
+
+int nfb_camera_rays(const nfb_camera* cam, long long first_pixel, long long count, float* origins,
+                    float* directions, float* pixels, void* stream) {
+  return launch_camera(cam, nullptr, first_pixel, count, origins, directions, pixels, stream);
+}
+
+int nfb_pixels_to_rays(const nfb_camera* cam, const float* pixels, long long n, float* directions,
+                       void* stream) {
+  if (!pixels && n > 0) return fail("null argument");
+  return launch_camera(cam, pixels, 0, n, nullptr, directions, nullptr, stream);
+}
 
 int nfb_set_trace(nfb_handle* h, long long* buffer, int capacity) {
   if (!h) return fail("null handle");

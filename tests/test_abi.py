@@ -51,3 +51,39 @@ def test_no_device_is_a_loud_error():
   h = ctypes.c_void_p()
   assert lib.nfb_create(ctypes.byref(cfg), 4, ctypes.byref(h)) != 0
   assert b'no CUDA device' in lib.nfb_last_error()
+
+
+def test_camera_struct_matches_header():
+  text = open(os.path.join(REPO, 'include', 'nerfies_b200.h')).read()
+  body = re.search(r'typedef struct nfb_camera \{(.*?)\} nfb_camera;', text, re.S).group(1)
+  body = re.sub(r'/\*.*?\*/', '', body, flags=re.S)
+  fields = []
+  for decl in body.split(';'):
+    decl = decl.strip()
+    if not decl:
+      continue
+    m = re.match(r'(int|float)\s+([a-z_]+)(?:\[(\d+)\])?$', decl)
+    assert m, decl
+    fields.append((m.group(2), m.group(1), int(m.group(3) or 1)))
+  got = []
+  for name, ctype in _lib.NfbCamera._fields_:
+    n = getattr(ctype, '_length_', 1)
+    base = ctype._type_ if n > 1 or hasattr(ctype, '_length_') else ctype
+    got.append((name, 'float' if base is ctypes.c_float else 'int', n))
+  assert fields == got
+  assert ctypes.sizeof(_lib.NfbCamera) == 4 * sum(n for _, _, n in fields)
+
+
+def test_camera_entry_points_fail_loudly_without_a_device():
+  import torch
+  if torch.cuda.is_available():
+    return
+  lib = _lib.load()
+  cam = _lib.NfbCamera()
+  cam.focal_length = 100.0
+  cam.pixel_aspect_ratio = 1.0
+  cam.image_size[:] = [4, 4]
+  assert lib.nfb_camera_rays(ctypes.byref(cam), 0, 16, None, ctypes.c_void_p(16), None, None) != 0
+  assert b'no CUDA device' in lib.nfb_last_error()
+  assert lib.nfb_camera_rays(ctypes.byref(cam), 10, 16, None, ctypes.c_void_p(16), None, None) != 0
+  assert b'exceeds' in lib.nfb_last_error()

@@ -52,9 +52,8 @@ __device__ __forceinline__ void undistort_point(float xd, float yd, float k1, fl
   xo = x; yo = y;
 }
 
-__global__ void __launch_bounds__(256) camera_rays_kernel(const CameraArgs a) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= a.count) return;
+// One pixel: unit world-space direction and the pixel position used.
+__device__ __forceinline__ void camera_ray_of_pixel(const CameraArgs& a, long long i, float* out_d, float* out_p) {
   const nfb_camera& c = a.cam;
   float px, py;
   if (a.pixels_in) {
@@ -82,14 +81,47 @@ __global__ void __launch_bounds__(256) camera_rays_kernel(const CameraArgs a) {
     d[j] = c.orientation[j] * l0 + c.orientation[3 + j] * l1 + c.orientation[6 + j] * l2;
   const float n2 = sqrtf(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);        // camera.py:266
 #pragma unroll
-  for (int j = 0; j < 3; ++j) a.directions[3 * i + j] = d[j] / n2;
-  if (a.origins) {
-#pragma unroll
-    for (int j = 0; j < 3; ++j) a.origins[3 * i + j] = c.position[j];   // datasets/core.py:66-67
-  }
-  if (a.pixels_out) {
-    a.pixels_out[2 * i] = px;
-    a.pixels_out[2 * i + 1] = py;
+  for (int j = 0; j < 3; ++j) d[j] = d[j] / n2;
+  out_d[0] = d[0]; out_d[1] = d[1]; out_d[2] = d[2];
+  out_p[0] = px; out_p[1] = py;
+}
+
+// 12-byte-per-pixel outputs are staged through shared memory so that a block
+// writes its 256 x 12 B as 192 aligned 16-byte vectors (a per-thread stride-12
+// scalar store pattern leaves HBM sectors partially written: 208 GB/s measured on
+// an 8K frame before this, see profiles/).
+__global__ void __launch_bounds__(256) camera_rays_kernel(const CameraArgs a) {
+  __shared__ __align__(16) float s_dir[256 * 3];
+  const long long block0 = (long long)blockIdx.x * 256;
+  const long long i = block0 + threadIdx.x;
+  const bool valid = i < a.count;
+  float d[3] = {0.f, 0.f, 0.f}, p[2] = {0.f, 0.f};
+  if (valid) camera_ray_of_pixel(a, i, d, p);
+  s_dir[threadIdx.x * 3 + 0] = d[0];
+  s_dir[threadIdx.x * 3 + 1] = d[1];
+  s_dir[threadIdx.x * 3 + 2] = d[2];
+  if (valid && a.pixels_out)
+    reinterpret_cast<float2*>(a.pixels_out)[i] = make_float2(p[0], p[1]);   // 8 B/thread: coalesced as is
+  __syncthreads();
+  const long long n_here = min((long long)256, a.count - block0);          // pixels of this block
+  if (n_here == 256) {
+    // block0 * 12 B is a multiple of 3072 B: 16-byte aligned if the buffer is
+    if (threadIdx.x < 192) {
+      reinterpret_cast<float4*>(a.directions + block0 * 3)[threadIdx.x] =
+          reinterpret_cast<const float4*>(s_dir)[threadIdx.x];
+      if (a.origins) {
+        // origins repeat (x,y,z): element e of the block's 768 floats is position[e % 3]
+        const int e = threadIdx.x * 4;
+        const float* q = a.cam.position;
+        reinterpret_cast<float4*>(a.origins + block0 * 3)[threadIdx.x] =
+            make_float4(q[e % 3], q[(e + 1) % 3], q[(e + 2) % 3], q[(e + 3) % 3]);   // datasets/core.py:66-67
+      }
+    }
+  } else {
+    for (int e = threadIdx.x; e < n_here * 3; e += 256) {
+      a.directions[block0 * 3 + e] = s_dir[e];
+      if (a.origins) a.origins[block0 * 3 + e] = a.cam.position[e % 3];
+    }
   }
 }
 

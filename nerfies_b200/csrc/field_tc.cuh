@@ -333,10 +333,13 @@ field_tc_kernel(const __grid_constant__ TcProgram prog, const __grid_constant__ 
     // ===================== MMA issuer =====================
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kCtlRegs));
     // One elected lane walks the flattened, host-precomputed schedule (TcUnit).
-    // Per unit: one issue_unit() block (fence, look-ahead probes of the next unit's
-    // barriers, 8 tcgen05.mma, the stage-release commit).  The code between two
-    // issue blocks is a handful of instructions: a single thread runs alone here,
-    // every dependent instruction on this path is ~5 idle cycles of the tensor pipe.
+    // Per unit: issue_half0() (fence + the 4 MMAs of sub-tile 0), then the table
+    // fetch and next-operand arithmetic in the shadow of those MMAs, then
+    // issue_half1() (look-ahead probes of the next unit's barriers, the 4 MMAs of
+    // sub-tile 1, the stage-release commit and the optional accumulator / x_free
+    // commits).  A single thread runs alone here: every dependent instruction on
+    // this path is ~5 idle cycles of the tensor pipe, so there are no function calls
+    // and the slow path (a barrier that is not ready yet) is out of line.
     if (elect_one()) {
       Tracer tr(args, 0);
       const uint64_t desc_hi = make_smem_desc(0) & 0xFFFFFFFF00000000ull;   // SBO/version/layout

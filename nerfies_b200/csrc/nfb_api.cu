@@ -412,7 +412,7 @@ long long nfb_kernel_launches(const nfb_handle* h) { return h ? h->launches : 0;
 
 static int launch_camera(const nfb_camera* cam, const float* pixels_in, long long first, long long count,
                          float* origins, float* directions, float* pixels_out, void* stream) {
-  if (!cam || !directions) return fail("null argument");
+  if (!cam) return fail("null argument");
   if (count < 0 || first < 0) return fail("negative pixel range");
   if (cam->image_size[0] < 1 || cam->image_size[1] < 1) return fail("image_size must be positive");
   if (!pixels_in && first + count > (long long)cam->image_size[0] * cam->image_size[1])
@@ -423,6 +423,10 @@ static int launch_camera(const nfb_camera* cam, const float* pixels_in, long lon
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
     return fail("no CUDA device: nerfies_b200 has no CPU path");
   if (count == 0) return 0;
+  if (!directions) return fail("null argument");
+  if ((reinterpret_cast<uintptr_t>(directions) | reinterpret_cast<uintptr_t>(origins)) & 15)
+    return fail("origins / directions must be 16-byte aligned");
+  if (reinterpret_cast<uintptr_t>(pixels_out) & 7) return fail("pixels must be 8-byte aligned");
   nfb::CameraArgs a{};
   a.cam = *cam; a.pixels_in = pixels_in; a.first = first; a.count = count;
   a.origins = origins; a.directions = directions; a.pixels_out = pixels_out;

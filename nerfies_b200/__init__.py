@@ -13,6 +13,7 @@ from nerfies_b200 import models  # noqa: F401
 from nerfies_b200 import model_utils  # noqa: F401
 from nerfies_b200 import evaluation  # noqa: F401
 from nerfies_b200 import camera  # noqa: F401
+from nerfies_b200 import checkpoints  # noqa: F401
 from nerfies_b200.models import construct_nerf, NerfModel  # noqa: F401
 
 __version__ = '0.1'

@@ -75,6 +75,12 @@ typedef struct nfb_config {
 /* Flags for the render entry points. */
 #define NFB_FLAG_COARSE_ONLY 1u  /* stop after the coarse level                 */
 #define NFB_FLAG_NO_WARP     2u  /* use_warp=False call-time override (models.py:321) */
+#define NFB_FLAG_METADATA_ENCODED 4u /* metadata_encoded=True (models.py:198-213,251;
+                                      * warping.py:186-187): warp_id / app_id / cam_id are
+                                      * reinterpreted as const float* per-ray embeddings of
+                                      * shape (B, num_warp_features) / (B, num_appearance_features) /
+                                      * (B, num_camera_features) and used instead of the GLO
+                                      * table rows.  Device entry points only. */
 
 /* Lifetime.  Replaces construct_nerf's model construction (models.py:424-463);
  * max_rays bounds B of every later call (workspace is sized once, here). */

@@ -26,6 +26,7 @@ WARP_TYPES = {None: 0, 'none': 0, 'translation': 1, 'se3': 2}
 PRECISIONS = {'fp32': 0, 'bf16': 1, 'bf16x3': 2}
 FLAG_COARSE_ONLY = 1
 FLAG_NO_WARP = 2
+FLAG_METADATA_ENCODED = 4
 
 
 class NfbConfig(ctypes.Structure):

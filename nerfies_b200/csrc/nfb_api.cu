@@ -282,7 +282,7 @@ int launch_check(nfb_handle* h, const char* what) {
 }
 
 int run_cond(nfb_handle* h, int B, const float* viewdirs, const unsigned* warp_id,
-             const unsigned* app_id, const unsigned* cam_id, cudaStream_t s) {
+             const unsigned* app_id, const unsigned* cam_id, cudaStream_t s, bool encoded = false) {
   const nfb_config& c = h->cfg;
   nfb::CondArgs a{};
   a.viewdirs = viewdirs; a.warp_id = warp_id; a.app_id = app_id; a.cam_id = cam_id;
@@ -293,6 +293,7 @@ int run_cond(nfb_handle* h, int B, const float* viewdirs, const unsigned* warp_i
   a.use_viewdirs = c.use_viewdirs; a.use_app = c.use_appearance_metadata; a.use_cam = c.use_camera_metadata;
   a.use_trunk_c = c.use_trunk_condition; a.use_alpha_c = c.use_alpha_condition;
   a.stride = h->cond_stride; a.cond = h->d_cond; a.num_rays = B;
+  a.encoded = encoded;
   if (h->prog[0].G + h->prog[0].tc + h->prog[0].ac + h->prog[0].rc == 0) return 0;
   const long long total = (long long)B * a.stride;
   nfb::ray_cond_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(a);
@@ -675,7 +676,8 @@ int nfb_render_samples(nfb_handle* h, int level, int B, int S, const float* z_va
   if (B == 0) return 0;
   cudaStream_t s = (cudaStream_t)stream;
   if (set_window(h, warp_alpha, s)) return -1;
-  if (run_cond(h, B, viewdirs ? viewdirs : directions, warp_id, app_id, cam_id, s)) return -1;
+  if (run_cond(h, B, viewdirs ? viewdirs : directions, warp_id, app_id, cam_id, s,
+               (flags & NFB_FLAG_METADATA_ENCODED) != 0)) return -1;
   float* smp = samples ? samples : h->d_samples;
   const bool use_warp = !(flags & NFB_FLAG_NO_WARP);
   if (run_field(h, level, (long long)B * S, S, origins, directions, z_vals, smp, warped_points,
@@ -697,7 +699,8 @@ int nfb_render_forward(nfb_handle* h, int B, const float* origins, const float* 
   const bool use_warp = !(flags & NFB_FLAG_NO_WARP);
   const bool fine = c.num_fine_samples > 0 && !(flags & NFB_FLAG_COARSE_ONLY);
   if (set_window(h, warp_alpha, s)) return -1;
-  if (run_cond(h, B, viewdirs ? viewdirs : directions, warp_id, app_id, cam_id, s)) return -1;
+  if (run_cond(h, B, viewdirs ? viewdirs : directions, warp_id, app_id, cam_id, s,
+               (flags & NFB_FLAG_METADATA_ENCODED) != 0)) return -1;
   // coarse level (models.py:332-349)
   if (nfb_coarse_z_vals(h, B, t_rand, h->d_zc, stream)) return -1;
   if (run_field(h, 0, (long long)B * nc, nc, origins, directions, h->d_zc, h->d_samples, nullptr,
@@ -720,6 +723,8 @@ int nfb_render_forward_host(nfb_handle* h, int B, const float* origins, const fl
                             const unsigned* app_id, const unsigned* cam_id, float warp_alpha,
                             unsigned flags, float* out_coarse, float* out_fine, void* stream) {
   if (check_call(h, B)) return -1;
+  if (flags & NFB_FLAG_METADATA_ENCODED)
+    return fail("NFB_FLAG_METADATA_ENCODED is only supported by the device entry points");
   if (B == 0) return 0;
   cudaStream_t s = (cudaStream_t)stream;
   const size_t mr = h->max_rays;

@@ -28,6 +28,7 @@ struct CondArgs {
   int stride;
   float* cond;                    // (B, stride)
   int num_rays;
+  int encoded;                    // metadata_encoded=True: the id pointers are (B, G|A|C) float embeddings
 };
 
 __global__ void ray_cond_kernel(const CondArgs a) {
@@ -37,12 +38,18 @@ __global__ void ray_cond_kernel(const CondArgs a) {
   int q = (int)(idx - (long long)ray * a.stride);
   float v = 0.f;
   auto app = [&](int j) {
+    if (a.encoded && a.app_id)      // models.py:198-199
+      return reinterpret_cast<const float*>(a.app_id)[(size_t)ray * a.A + j];
     unsigned id = a.app_id ? a.app_id[ray] : 0u;
     id = min(id, (unsigned)(a.n_app - 1));
     return a.app_table[(size_t)id * a.A + j];
   };
   do {
     if (q < a.G) {
+      if (a.encoded && a.warp_id) {   // warping.py:186-187
+        v = reinterpret_cast<const float*>(a.warp_id)[(size_t)ray * a.G + q];
+        break;
+      }
       unsigned id = a.warp_id ? a.warp_id[ray] : 0u;
       id = min(id, (unsigned)(a.n_warp - 1));
       v = a.warp_table[(size_t)id * a.G + q];
@@ -65,6 +72,10 @@ __global__ void ray_cond_kernel(const CondArgs a) {
     q -= dv;
     if (q < ac) { v = app(q); break; }
     q -= ac;
+    if (a.encoded && a.cam_id) {      // models.py:210-211
+      v = reinterpret_cast<const float*>(a.cam_id)[(size_t)ray * a.C + q];
+      break;
+    }
     unsigned id = a.cam_id ? a.cam_id[ray] : 0u;
     id = min(id, (unsigned)(a.n_cam - 1));
     v = a.cam_table[(size_t)id * a.C + q];

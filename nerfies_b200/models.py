@@ -331,8 +331,6 @@ class NerfModel:
     uniform draws of the stratified path (used by the parity tests).
     """
     del deterministic, mutable  # unused by the reference's __call__ as well.
-    if metadata_encoded:
-      raise NotImplementedError('metadata_encoded=True is not implemented')
     if return_warp_jacobian or self.use_warp_jacobian:
       raise NotImplementedError(
           'warp Jacobians (jax.jacfwd, warping.py:385-387) belong to the '
@@ -350,11 +348,29 @@ class NerfModel:
                 if 'viewdirs' in rays_dict else None)
     md = rays_dict.get('metadata', {})
     use_warp = self.use_warp and use_warp
-    warp_id = _prep_ids(md.get('warp'), dev) if self.use_warp else None
-    app_id = (_prep_ids(md.get('appearance'), dev)
-              if self.use_appearance_metadata else None)
-    cam_id = (_prep_ids(md.get('camera'), dev)
-              if self.use_camera_metadata else None)
+    if metadata_encoded:
+      # models.py:198-213,251 / warping.py:186-187: the metadata leaves are the
+      # per-ray embeddings themselves, (B, num_*_features) float32.
+      def enc(key, width, used):
+        if not used:
+          return None
+        v = md.get(key)
+        if v is None:
+          return None
+        v = _prep_f32(v, dev)
+        if v.shape != (B, width):
+          raise ValueError(f"metadata_encoded=True: metadata['{key}'] must be ({B}, {width}), "
+                           f'got {tuple(v.shape)}')
+        return v
+      warp_id = enc('warp', self.num_warp_features, self.use_warp)
+      app_id = enc('appearance', self.num_appearance_features, self.use_appearance_metadata)
+      cam_id = enc('camera', self.num_camera_features, self.use_camera_metadata)
+    else:
+      warp_id = _prep_ids(md.get('warp'), dev) if self.use_warp else None
+      app_id = (_prep_ids(md.get('appearance'), dev)
+                if self.use_appearance_metadata else None)
+      cam_id = (_prep_ids(md.get('camera'), dev)
+                if self.use_camera_metadata else None)
     if self.use_warp and use_warp and warp_id is None:
       raise KeyError("rays_dict['metadata']['warp'] is required")
     return_weights = self.use_weights or return_weights
@@ -370,6 +386,8 @@ class NerfModel:
     lib, h = hd.lib, hd.h
     nc, nf = self.num_coarse_samples, self.num_fine_samples
     flags = 0 if use_warp else _lib.FLAG_NO_WARP
+    if metadata_encoded:
+      flags |= _lib.FLAG_METADATA_ENCODED
     out = {}
     with torch.cuda.device(dev):
       out_c = torch.empty(B, 6, device=dev)

@@ -96,9 +96,14 @@ def to_numpy(tree):
       np.float32) for k, v in tree.items()}
 
 
+ONLY = set(sys.argv[1:])   # optional: names of the cases to (re)generate
+
+
 def make_case(name, cfg_kwargs, *, num_rays, n_app, n_cam, n_warp, near, far,
               warp_alpha, seed, trained_like=True, stratified=False,
-              oracle_param_seed=None, store_params=True):
+              oracle_param_seed=None, store_params=True, encoded=False):
+  if ONLY and name not in ONLY:
+    return
   cfg_kwargs = dict(cfg_kwargs)
   act = cfg_kwargs.pop('activation', 'relu')
   sact = cfg_kwargs.pop('sigma_activation', 'relu')
@@ -214,6 +219,23 @@ def make_case(name, cfg_kwargs, *, num_rays, n_app, n_cam, n_warp, near, far,
     blob['warp/ids'] = ids
     blob['warp/warped_points'] = np.asarray(wout['warped_points'], np.float32)
 
+  # metadata_encoded=True (models.py:198-213,251; warping.py:186-187): the metadata
+  # leaves are per-ray embeddings, deliberately NOT rows of the GLO tables.
+  if encoded:
+    rng = np.random.default_rng(seed + 4)
+    emb = {'warp': (rng.standard_normal((num_rays, cfg.num_warp_features)) * 0.05).astype(np.float32),
+           'appearance': (rng.standard_normal((num_rays, cfg.appearance_metadata_dims)) * 0.3).astype(np.float32),
+           'camera': (rng.standard_normal((num_rays, cfg.camera_metadata_dims)) * 0.3).astype(np.float32)}
+    erays = dict(rays, metadata=emb)
+    eout = model.apply({'params': params}, erays, warp_extra=warp_extra,
+                       rngs={'coarse': jax.random.PRNGKey(seed + 1), 'fine': jax.random.PRNGKey(seed + 2)},
+                       mutable=False, metadata_encoded=True, return_points=True, return_weights=True)
+    for k, v in emb.items():
+      blob[f'enc/metadata/{k}'] = v
+    for level, ret in eout.items():
+      for k, v in ret.items():
+        blob[f'enc/out/{level}/{k}'] = np.asarray(v, dtype=np.float32)
+
   path = os.path.join(REPO, 'tests', 'golden', name + '.npz')
   np.savez_compressed(path, **blob)
   print(f'{name}: {os.path.getsize(path) / 1024:.0f} KiB  '
@@ -280,6 +302,17 @@ def main():
       num_warp_freqs=8, sigma_activation='softplus'),
             num_rays=3, n_app=20, n_cam=1, n_warp=20, near=0.02, far=0.83,
             warp_alpha=2.25, seed=17, oracle_param_seed=17, store_params=False)
+
+
+  # H: metadata_encoded=True with warp + appearance + camera embeddings and the
+  #    alpha/rgb condition wiring (also stores the ordinary id-based run).
+  make_case('encoded_small', dict(
+      small, use_warp=True, warp_field_type='se3', num_nerf_point_freqs=8,
+      num_warp_freqs=8, use_appearance_metadata=True, use_camera_metadata=True,
+      use_alpha_condition=True, use_rgb_condition=True,
+      sigma_activation='softplus', warp_kwargs={'trunk_width': 32}),
+            num_rays=10, n_app=4, n_cam=3, n_warp=5, near=0.02, far=0.83,
+            warp_alpha=5.0, seed=18, encoded=True)
 
 
 if __name__ == '__main__':

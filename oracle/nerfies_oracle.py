@@ -544,7 +544,7 @@ def render_forward(params, spec: OracleSpec, rays_dict: Dict[str, Any],
 def render_level(params, spec: OracleSpec, level: str,
                  rays_dict: Dict[str, Any], z_vals: Tensor,
                  warp_alpha: float = 0.0, use_warp: bool = True,
-                 dtype=torch.float32) -> Dict[str, Tensor]:
+                 dtype=torch.float32, metadata_encoded: bool = False) -> Dict[str, Tensor]:
   """One level of NerfModel.__call__ for caller-supplied z_vals: points =
   o + z d (model_utils.py:72-73 / :214-215) then render_samples
   (models.py:230-287).  Used to test the levels in isolation."""
@@ -556,7 +556,7 @@ def render_level(params, spec: OracleSpec, level: str,
   points = origins[:, None, :] + z_vals[:, :, None] * directions[:, None, :]
   out = render_samples(tree_to(params, dtype), spec, level, points, z_vals,
                        directions, viewdirs, rays_dict.get('metadata', {}),
-                       warp_alpha, use_warp, False, True)
+                       warp_alpha, use_warp, metadata_encoded, True)
   out['z_vals'] = z_vals
   return out
 

@@ -11,7 +11,7 @@ from oracle import nerfies_oracle as O
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
 CASES = ['se3_small', 'translation_small', 'nowarp_variants',
          'alpha_cond_init', 'se3_stratified', 'quarterhd_dims',
-         'test_local_dims']
+         'test_local_dims', 'encoded_small']
 
 
 def unflatten(flat):
@@ -71,6 +71,15 @@ class Golden:
                           for k in z.files if k.startswith('out/')})
     self.t_rand = torch.from_numpy(z['t_rand']) if 't_rand' in z.files else None
     self.u_rand = torch.from_numpy(z['u_rand']) if 'u_rand' in z.files else None
+    # metadata_encoded=True run of the same model (encoded_small only)
+    self.enc = None
+    if any(k.startswith('enc/') for k in z.files):
+      self.enc = {
+          'metadata': {k.split('/')[-1]: torch.from_numpy(z[k]) for k in z.files
+                       if k.startswith('enc/metadata/')},
+          'out': unflatten({k[len('enc/out/'):]: torch.from_numpy(z[k])
+                            for k in z.files if k.startswith('enc/out/')}),
+      }
     self.warp = None
     if 'warp/points' in z.files:
       self.warp = {

@@ -96,3 +96,28 @@ def test_fp64_shadow_close_to_fp32():
                          dtype=torch.float64)
   for k in ('rgb', 'depth', 'acc'):
     assert rel_err(o32['coarse'][k], o64['coarse'][k]) < 1e-4
+
+
+def test_metadata_encoded_vs_reference_source():
+  """metadata_encoded=True (models.py:198-213,251; warping.py:186-187): per-ray
+  embeddings instead of GLO ids, run through the reference's own source."""
+  g = Golden('encoded_small')
+  rays = dict(g.rays, metadata=g.enc['metadata'])
+  out = O.render_forward(g.params, g.spec, rays, warp_alpha=g.warp_alpha,
+                         metadata_encoded=True, return_points=True)
+  for key, ref in g.enc['out']['coarse'].items():
+    err = rel_err(out['coarse'][key], ref)
+    assert err < TOL, f'encoded coarse/{key}: rel err {err:.3e}'
+  # the zero-argument fine z_vals are those sample_pdf produced in the encoded run
+  zf = out['fine']['z_vals']
+  fine = O.render_level(g.params, g.spec, 'fine', rays, zf, g.warp_alpha, metadata_encoded=True)
+  assert rel_err(out['fine']['rgb'], fine['rgb']) < 1e-6
+  assert rel_err(out['fine']['rgb'], g.enc['out']['fine']['rgb']) < TOL_E2E_RGB
+  # feeding the table rows as embeddings reproduces the id-based run exactly
+  p = g.params
+  emb = {'warp': p['warp_field']['metadata_encoder']['embed']['embedding'][g.rays['metadata']['warp'][:, 0].long()],
+         'appearance': p['appearance_encoder']['embed']['embedding'][g.rays['metadata']['appearance'][:, 0].long()],
+         'camera': p['camera_encoder']['embed']['embedding'][g.rays['metadata']['camera'][:, 0].long()]}
+  a = O.render_forward(p, g.spec, dict(g.rays, metadata=emb), warp_alpha=g.warp_alpha, metadata_encoded=True)
+  b = O.render_forward(p, g.spec, g.rays, warp_alpha=g.warp_alpha)
+  assert torch.equal(a['fine']['rgb'], b['fine']['rgb'])

@@ -186,6 +186,44 @@ def test_warp_forward(name):
   assert err < TOL, f'{name}: {err:.3e}'
 
 
+def test_metadata_encoded_apply():
+  """metadata_encoded=True through model.apply (NFB_FLAG_METADATA_ENCODED): vs the
+  reference source's encoded run, and bit-identical to the id path when the
+  embeddings handed in are the GLO table rows."""
+  g = Golden('encoded_small')
+  model = model_from_spec(g.spec_dict, device=DEV)
+  params = tree_to_device(g.params, DEV)
+  rays = dict(g.rays, metadata=g.enc['metadata'])
+  extra = {'alpha': g.warp_alpha, 'time_alpha': 0.0}
+  for return_points in (False, True):
+    out = model.apply({'params': params}, rays, warp_extra=extra, metadata_encoded=True,
+                      return_weights=True, return_points=return_points)
+    torch.cuda.synchronize()
+    for k in ('rgb', 'depth', 'acc', 'weights'):
+      err = rel_err(out['coarse'][k].cpu(), g.enc['out']['coarse'][k])
+      assert err < TOL, f'encoded coarse/{k}: {err:.3e}'
+    for k in ('rgb', 'depth', 'acc'):
+      err = rel_err(out['fine'][k].cpu(), g.enc['out']['fine'][k])
+      assert err < TOL_E2E, f'encoded fine/{k}: {err:.3e}'
+    if return_points:
+      err = rel_err(out['coarse']['warped_points'].cpu(), g.enc['out']['coarse']['warped_points'])
+      assert err < TOL, f'encoded warped points: {err:.3e}'
+  p = g.params
+  md = g.rays['metadata']
+  emb = {'warp': p['warp_field']['metadata_encoder']['embed']['embedding'][md['warp'][:, 0].long()],
+         'appearance': p['appearance_encoder']['embed']['embedding'][md['appearance'][:, 0].long()],
+         'camera': p['camera_encoder']['embed']['embedding'][md['camera'][:, 0].long()]}
+  a = model.apply({'params': params}, dict(g.rays, metadata=emb), warp_extra=extra, metadata_encoded=True)
+  b = model.apply({'params': params}, g.rays, warp_extra=extra)
+  torch.cuda.synchronize()
+  for lv in ('coarse', 'fine'):
+    for k in ('rgb', 'depth', 'acc'):
+      assert torch.equal(a[lv][k], b[lv][k]), (lv, k)
+  with pytest.raises(ValueError):
+    model.apply({'params': params}, dict(g.rays, metadata={**emb, 'warp': emb['warp'][:, :3]}),
+                warp_extra=extra, metadata_encoded=True)
+
+
 def test_use_warp_false_override():
   g = Golden('se3_small')
   model = model_from_spec(g.spec_dict, device=DEV)

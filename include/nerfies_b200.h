@@ -208,6 +208,15 @@ int nfb_selftest_gemm(int K, int N, const float* A, const float* W, float* C,
  * cycles, work items, issue cycles. */
 int nfb_selftest_microbench(int mode, int n, int reps, int nwarps, long long* out);
 
+/* CTA-pair (tcgen05 cta_group::2, a 2-CTA cluster) variant of nfb_selftest_gemm:
+ * C (256 x N) = bf16(A (256 x K)) x bf16(W (K x N)) times `reps`, N in {64,128,256},
+ * K <= 320.  out (host, 2 x int64, nullable): cycles seen by the leader CTA from
+ * the first MMA issue to completion, and the number of MMAs (M=256, K=16) issued.
+ * Hardware self-test / micro-benchmark for the planned 2-CTA field kernel; no
+ * reference analogue. */
+int nfb_selftest_gemm2(int K, int N, const float* A, const float* W, float* C, int reps,
+                       long long* out, void* stream);
+
 /* Number of CUDA kernels this handle has launched so far (bench accounting). */
 long long nfb_kernel_launches(const nfb_handle* h);
 /* Thread-local description of the last error returned on this thread. */

@@ -17,7 +17,7 @@ SYMBOLS = [
     'nfb_render_samples', 'nfb_sample_pdf', 'nfb_coarse_z_vals',
     'nfb_warp_forward', 'nfb_kernel_launches', 'nfb_last_error', 'nfb_version',
     'nfb_set_profiling', 'nfb_field_time_ms', 'nfb_selftest_gemm', 'nfb_set_trace', 'nfb_selftest_microbench',
-    'nfb_camera_rays', 'nfb_pixels_to_rays',
+    'nfb_camera_rays', 'nfb_pixels_to_rays', 'nfb_selftest_gemm2',
 ]
 
 ACTIVATIONS = {'none': 0, 'relu': 1, 'elu': 2, 'leaky_relu': 3, 'tanh': 4,
@@ -150,6 +150,8 @@ def load():
   lib.nfb_camera_rays.restype = ci
   lib.nfb_pixels_to_rays.argtypes = [ctypes.POINTER(NfbCamera), vp, ll, vp, vp]
   lib.nfb_pixels_to_rays.restype = ci
+  lib.nfb_selftest_gemm2.argtypes = [ci, ci, vp, vp, vp, ci, vp, vp]
+  lib.nfb_selftest_gemm2.restype = ci
   lib.nfb_last_error.argtypes = []
   lib.nfb_last_error.restype = ctypes.c_char_p
   lib.nfb_version.argtypes = []

@@ -18,6 +18,7 @@
 #include "camera_kernels.cuh"
 #include "tc_common.cuh"
 #include "tc_selftest.cuh"
+#include "tc_selftest2.cuh"
 #ifdef NFB_WITH_TC
 #include "field_tc.cuh"
 #endif
@@ -505,6 +506,38 @@ int nfb_selftest_gemm(int K, int N, const float* A, const float* W, float* C, vo
   cudaFree(d_map);
   cudaFree(d_w);
   if (e != cudaSuccess) return fail("selftest kernel failed: %s", cudaGetErrorString(e));
+  return abort_check();
+}
+
+int nfb_selftest_gemm2(int K, int N, const float* A, const float* W, float* C, int reps, long long* out,
+                       void* stream) {
+  using namespace nfb::tc;
+  if (K < 1 || K > kSelfMaxKb * kBlockK || (N != 64 && N != 128 && N != 256)) return fail("selftest2: K<=320, N in {64,128,256}");
+  if (reps < 1) return fail("selftest2: reps must be >= 1");
+  if (ensure_abort_flag() || abort_check()) return -1;
+  cudaStream_t s = (cudaStream_t)stream;
+  const int nkb = (K + kBlockK - 1) / kBlockK;
+  std::vector<int> k_map(nkb * kBlockK, -1);
+  for (int k = 0; k < K; ++k) k_map[k] = k;
+  int* d_map = nullptr;
+  __nv_bfloat16* d_w = nullptr;
+  long long* d_out = nullptr;
+  NFB_CUDA(cudaMalloc(&d_map, k_map.size() * sizeof(int)));
+  NFB_CUDA(cudaMalloc(&d_w, (size_t)nkb * N * kRowBytes));
+  NFB_CUDA(cudaMalloc(&d_out, 2 * sizeof(long long)));
+  NFB_CUDA(cudaMemsetAsync(d_out, 0, 2 * sizeof(long long), s));
+  NFB_CUDA(cudaMemcpyAsync(d_map, k_map.data(), k_map.size() * sizeof(int), cudaMemcpyHostToDevice, s));
+  const long long total = (long long)nkb * N * kBlockK;
+  pack_weight_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(W, N, d_map, nkb, N, N, d_w);
+  NFB_CUDA(cudaFuncSetAttribute(tc_selftest2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSelf2SmemBytes));
+  tc_selftest2_kernel<<<2, 160, kSelf2SmemBytes, s>>>(A, K, d_w, nkb, N, C, reps, d_out);
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+  long long h_out[2] = {0, 0};
+  if (e == cudaSuccess) e = cudaMemcpy(h_out, d_out, sizeof(h_out), cudaMemcpyDeviceToHost);
+  cudaFree(d_map); cudaFree(d_w); cudaFree(d_out);
+  if (e != cudaSuccess) return fail("selftest2 kernel failed: %s", cudaGetErrorString(e));
+  if (out) { out[0] = h_out[0]; out[1] = h_out[1]; }
   return abort_check();
 }
 

@@ -151,6 +151,26 @@ def test_coarse_z_and_resample(name):
     assert float(res.max()) < 5e-6, (name, b, float(res.max()))
 
 
+_E2E_BAND = {}
+
+
+def _e2e_tol(g, key, encoded=False):
+  """End-to-end tolerance through the ill-conditioned inverse-CDF resampling.
+
+  TOL_E2E, or three times the distance between the fixture (the reference's fp32 numpy
+  run) and the oracle's fp64 shadow on the same inputs when that is larger: no
+  fp32 implementation can agree with the fixture better than exact arithmetic
+  does (e.g. 2.0e-3 on `acc` for encoded_small)."""
+  ck = (g.name, encoded)
+  if ck not in _E2E_BAND:
+    rays = dict(g.rays, metadata=g.enc['metadata']) if encoded else g.rays
+    ref = (g.enc['out'] if encoded else g.out)['fine']
+    o64 = O.render_forward(g.params, g.spec, rays, warp_alpha=g.warp_alpha, metadata_encoded=encoded,
+                           t_rand=g.t_rand, u_rand=g.u_rand, dtype=torch.float64)['fine']
+    _E2E_BAND[ck] = {k: rel_err(o64[k], ref[k]) for k in ('rgb', 'depth', 'acc')}
+  return max(TOL_E2E, 3.0 * _E2E_BAND[ck][key])
+
+
 @pytest.mark.parametrize('name', CASES)
 def test_end_to_end_apply(name):
   g = Golden(name)
@@ -166,7 +186,7 @@ def test_end_to_end_apply(name):
       assert rel_err(out['coarse'][k].cpu(), g.out['coarse'][k]) < TOL
     for k in ('rgb', 'depth', 'acc'):
       err = rel_err(out['fine'][k].cpu(), g.out['fine'][k])
-      assert err < TOL_E2E, f'{name} fine/{k}: {err:.3e}'
+      assert err < _e2e_tol(g, k), f'{name} fine/{k}: {err:.3e} (tol {_e2e_tol(g, k):.1e})'
     if return_points:
       assert rel_err(out['coarse']['points'].cpu(),
                      g.out['coarse']['points']) < 1e-6
@@ -204,7 +224,8 @@ def test_metadata_encoded_apply():
       assert err < TOL, f'encoded coarse/{k}: {err:.3e}'
     for k in ('rgb', 'depth', 'acc'):
       err = rel_err(out['fine'][k].cpu(), g.enc['out']['fine'][k])
-      assert err < TOL_E2E, f'encoded fine/{k}: {err:.3e}'
+      tol = _e2e_tol(g, k, encoded=True)
+      assert err < tol, f'encoded fine/{k}: {err:.3e} (tol {tol:.1e})'
     if return_points:
       err = rel_err(out['coarse']['warped_points'].cpu(), g.enc['out']['coarse']['warped_points'])
       assert err < TOL, f'encoded warped points: {err:.3e}'

@@ -246,7 +246,16 @@ __device__ __forceinline__ void cond_to_block(uint8_t* block, int r, const float
 // kH = epilogue threads per row: 1 (8 epilogue warps) or 2 (16 warps; the two
 // threads of a row are in warps w and w+4 - same TMEM lane quarter - and split
 // every chunk's columns; the per-row scalar work is done redundantly by both).
-template <int kH>
+// kPair: the CTA-pair variant (cluster of 2, tcgen05 cta_group::2).  Every CTA
+// still owns two 128-row sub-tiles, its activations, its TMEM and its epilogue
+// warps; an MMA is M = 256 across the two CTAs' sub-tiles and each CTA stages only
+// its half (chunk_n / 2 rows) of every weight unit.  Only the leader CTA (cluster
+// rank 0) issues MMAs; every commit is multicast to both CTAs' barriers.  The
+// leader's issuer also needs the follower's "weights landed" and "activations
+// ready" events: the follower's otherwise idle issuer warp walks the same unit
+// table, waits on its local barriers and forwards each event with one remote
+// mbarrier arrive (the leader's full / x_ready barriers count one extra arrival).
+template <int kH, bool kPair = false>
 __global__ void __launch_bounds__(32 * (8 * kH + 4), 1)
 field_tc_kernel(const __grid_constant__ TcProgram prog, const __grid_constant__ TcBias biasp,
                 const FieldArgs args, const uint8_t* __restrict__ wpack,
@@ -266,18 +275,28 @@ field_tc_kernel(const __grid_constant__ TcProgram prog, const __grid_constant__ 
   TcBars* bars = reinterpret_cast<TcBars*>(reinterpret_cast<uint8_t*>(alpha_s) + kAlphaBytes);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t rank = kPair ? cluster_ctarank() : 0u;      // 0 = leader (issues the MMAs)
+  const bool leader = rank == 0;
   if (tid == kMmaWarp * 32) {
-    for (int i = 0; i < kStages; ++i) { mbar_init(&bars->full[i], 1); mbar_init(&bars->empty[i], 1); }
+    const uint32_t relay = (kPair && leader) ? 1u : 0u;       // + the follower's forwarded arrival
+    for (int i = 0; i < kStages; ++i) { mbar_init(&bars->full[i], 1 + relay); mbar_init(&bars->empty[i], 1); }
     mbar_init(&bars->acc_ready[0], 1); mbar_init(&bars->acc_ready[1], 1);
     mbar_init(&bars->x_free, 1);
-    for (int k = 0; k < 3; ++k) mbar_init(&bars->x_ready[k], kEpiThreads);
+    for (int k = 0; k < 3; ++k) mbar_init(&bars->x_ready[k], kEpiThreads + relay);
     mbar_init(&bars->never, 1);
     fence_barrier_init();
   }
-  if (warp == kMmaWarp) tmem_alloc(&bars->tmem_slot, 512);
+  if (warp == kMmaWarp) {
+    if constexpr (kPair) tmem_alloc2(&bars->tmem_slot, 512);
+    else tmem_alloc(&bars->tmem_slot, 512);
+  }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (kPair) cluster_sync_all();   // the peer's barriers are initialised before any remote arrival
+  else __syncthreads();
   tc_fence_after();
+  // The follower's pair index is the leader's + 1: both CTAs run the same number of
+  // iterations (rows beyond the end are clamped and never stored).
+  const int pair_lim = num_pairs + (int)rank;
   const uint32_t tmem_base = bars->tmem_slot;
   const bool do_warp = args.use_warp && prog.warp_type != 0;
   // Steps executed per tile pair: the warp net's steps come first in the list.
@@ -309,11 +328,13 @@ field_tc_kernel(const __grid_constant__ TcProgram prog, const __grid_constant__ 
     {
       Tracer tr(args, lane == 0 ? 3 : -1);
       uint32_t it = 0, dead = 0;                       // dead: see mbar_wait()
-      for (int pair = blockIdx.x; pair < num_pairs; pair += gridDim.x) {
+      for (int pair = blockIdx.x; pair < pair_lim; pair += gridDim.x) {
         for (int si = first_step; si <= last_step; ++si) {
           const TcStep& st = prog.steps[si];
-          const uint32_t bytes = (uint32_t)st.chunk_n * kRowBytes;
-          const uint8_t* src = wpack + st.w_off;
+          const uint32_t unit_bytes = (uint32_t)st.chunk_n * kRowBytes;
+          // CTA pair: this CTA's half of every unit (rows rank*chunk_n/2 ..)
+          const uint32_t bytes = kPair ? unit_bytes / 2 : unit_bytes;
+          const uint8_t* src = wpack + st.w_off + (kPair ? rank * bytes : 0u);
           for (int u = 0; u < st.n_chunks * st.nkb; ++u, ++it) {
             const int sg = it % kStages;
             const uint32_t ph = (it / kStages) & 1;
@@ -321,7 +342,7 @@ field_tc_kernel(const __grid_constant__ TcProgram prog, const __grid_constant__ 
             tr.ev(si, u);
             if (elect_one()) {
               mbar_arrive_expect_tx(&bars->full[sg], bytes);
-              bulk_g2s(stages + sg * kStageBytes, src + (size_t)u * bytes, bytes, &bars->full[sg]);
+              bulk_g2s(stages + sg * kStageBytes, src + (size_t)u * unit_bytes, bytes, &bars->full[sg]);
             }
             __syncwarp();
           }
@@ -329,6 +350,28 @@ field_tc_kernel(const __grid_constant__ TcProgram prog, const __grid_constant__ 
       }
       if (lane == 0) tr.finish(args, 3);
     }
+  } else if (kPair && warp == kMmaWarp && !leader) {
+    // ===================== follower CTA: event relay =====================
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kCtlRegs));
+    if (elect_one()) {
+      const int u_begin = prog.unit_begin[first_step], u_end = prog.unit_begin[last_step + 1];
+      uint32_t sg = 0, wph = 0, xr = 0, dead = 0;
+      for (int pair = blockIdx.x; pair < pair_lim; pair += gridDim.x) {
+        for (int u = u_begin; u < u_end; ++u) {
+          const uint32_t flags = prog.units[u].flags;
+          // in the order the leader's issuer consumes them
+          if (flags & kUWaitX0) { mbar_wait(&bars->x_ready[0], xr & 1, dead); mbar_arrive_remote(&bars->x_ready[0], 0); }
+          if (flags & kUWaitX1) { mbar_wait(&bars->x_ready[1], xr & 1, dead); mbar_arrive_remote(&bars->x_ready[1], 0); }
+          if (flags & kUWaitX2) { mbar_wait(&bars->x_ready[2], xr & 1, dead); mbar_arrive_remote(&bars->x_ready[2], 0); }
+          mbar_wait(&bars->full[sg], wph, dead);
+          mbar_arrive_remote(&bars->full[sg], 0);
+          sg = (sg + 1) & (kStages - 1);
+          wph ^= (sg == 0 ? 1u : 0u);
+          xr += (flags & kUStepEnd) ? 1u : 0u;
+        }
+      }
+    }
+    __syncwarp();
   } else if (warp == kMmaWarp) {
     // ===================== MMA issuer =====================
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kCtlRegs));
@@ -364,7 +407,9 @@ field_tc_kernel(const __grid_constant__ TcProgram prog, const __grid_constant__ 
       uint32_t d0 = tmem_base + c0.z;
       uint64_t bd = desc_hi | (uint64_t)st_lo;
       uint64_t ad0 = desc_hi | (uint64_t)(lo_base + c0.x);
-      for (int pair = blockIdx.x; pair < num_pairs; pair += gridDim.x) {
+      // cta_group::2: M = 256 in the instruction descriptor (bits 24..28 hold M >> 4)
+      constexpr uint32_t kIdescPair = kPair ? (8u << 24) : 0u;
+      for (int pair = blockIdx.x; pair < pair_lim; pair += gridDim.x) {
         for (int u = u_begin; u < u_end; ++u) {
           const uint32_t flags = c1.x, need = c1.y;
           if ((ready & need) != need) {                    // slow path: something is not there yet
@@ -373,7 +418,8 @@ field_tc_kernel(const __grid_constant__ TcProgram prog, const __grid_constant__ 
             if ((need & 8) && !(ready & 8)) mbar_wait_issuer(&bars->x_ready[2], xr & 1, dead);
             if (!(ready & 1)) mbar_wait_issuer(&bars->full[sg], wph, dead);
           }
-          issue_half0(d0, ad0, bd, c0.w, flags & kUAccum);
+          if constexpr (kPair) issue_half0_pair(d0, ad0, bd, c0.w + kIdescPair, flags & kUAccum);
+          else issue_half0(d0, ad0, bd, c0.w, flags & kUAccum);
           // ---- bookkeeping while sub-tile 0's MMAs execute ----
           if (++un >= u_end) un -= n_u;
           const uint4 f0 = utab[2 * un], f1 = utab[2 * un + 1];     // table entry two units ahead
@@ -383,13 +429,18 @@ field_tc_kernel(const __grid_constant__ TcProgram prog, const __grid_constant__ 
           const uint64_t ad1 = desc_hi | (uint64_t)(lo_base + c0.y);
           const uint32_t px0 = (c1.z & 2) ? b_x0 : 0u, px1 = (c1.z & 4) ? b_x1 : 0u;
           const uint32_t px2 = (c1.z & 8) ? b_x2 : 0u;
-          const uint32_t d1 = d0 + 256, idesc = c0.w, bar_e = b_empty + sg * 8;
+          const uint32_t d1 = d0 + 256, idesc = c0.w + kIdescPair, bar_e = b_empty + sg * 8;
           const uint64_t bd_cur = bd;
           // next unit's first-half operands
           d0 = tmem_base + n0.z;
           bd = desc_hi | (uint64_t)(st_lo + nsg * (kStageBytes >> 4));
           ad0 = desc_hi | (uint64_t)(lo_base + n0.x);
-          if (flags & (kUCommitXFree | kUCommitAcc0 | kUCommitAcc1)) {
+          if constexpr (kPair) {
+            ready = issue_half1_pair(d1, ad1, bd_cur, idesc, flags & kUAccum, bar_e,
+                                     (flags & kUCommitXFree) ? b_xfree : 0u,
+                                     (flags & kUCommitAcc0) ? b_acc0 : ((flags & kUCommitAcc1) ? b_acc1 : 0u),
+                                     b_full + nsg * 8, nwph, px0, px1, px2, nxr & 1);
+          } else if (flags & (kUCommitXFree | kUCommitAcc0 | kUCommitAcc1)) {
             ready = issue_half1<true>(d1, ad1, bd_cur, idesc, flags & kUAccum, bar_e,
                                       (flags & kUCommitXFree) ? b_xfree : 0u,
                                       (flags & kUCommitAcc0) ? b_acc0 : ((flags & kUCommitAcc1) ? b_acc1 : 0u),
@@ -471,11 +522,11 @@ field_tc_kernel(const __grid_constant__ TcProgram prog, const __grid_constant__ 
 
     int pair = blockIdx.x;
     epi_sync();                                        // alpha_s is visible to every epilogue thread
-    if (pair < num_pairs) {
+    if (pair < pair_lim) {
       begin_pair(pair);
       arrive_both();
     }
-    for (; pair < num_pairs; pair += gridDim.x) {
+    for (; pair < pair_lim; pair += gridDim.x) {
       for (int si = first_step; si <= last_step; ++si) {
         const TcStep& st = prog.steps[si];
         const float4* bias4 = biasp.b4 + si * 64;     // this step's 256 biases (kernel-parameter constant bank)
@@ -691,7 +742,7 @@ field_tc_kernel(const __grid_constant__ TcProgram prog, const __grid_constant__ 
             if (args.warp_only) {
               // next pair's first input block, then hand over
               const int nxt = pair + gridDim.x;
-              if (nxt < num_pairs) begin_pair(nxt);
+              if (nxt < pair_lim) begin_pair(nxt);
             } else {
               if (args.fast_encode) posenc_fast_to_block(ins, r, row.x, prog.Fp, nullptr, nullptr, 0, cb, ce);
               else posenc_to_block(ins, r, row.x, prog.Fp, nullptr, nullptr, 0, cb, ce);
@@ -705,7 +756,7 @@ field_tc_kernel(const __grid_constant__ TcProgram prog, const __grid_constant__ 
               reinterpret_cast<float4*>(args.samples)[row.m] = o;
             }
             const int nxt = pair + gridDim.x;
-            if (nxt < num_pairs) begin_pair(nxt);
+            if (nxt < pair_lim) begin_pair(nxt);
             arrive_both();
             tr.ev(si, 5);
           }
@@ -716,8 +767,13 @@ field_tc_kernel(const __grid_constant__ TcProgram prog, const __grid_constant__ 
     if (sink == 0x9e3779b9u && args.trace) args.trace[0] = sink;   // never true in practice
     tc_fence_before();
   }
-  __syncthreads();
-  if (warp == kMmaWarp) tmem_dealloc(tmem_base, 512);
+  if constexpr (kPair) {
+    cluster_sync_all();        // nobody frees TMEM or exits while the peer still computes or signals
+    if (warp == kMmaWarp) tmem_dealloc2(tmem_base, 512);
+  } else {
+    __syncthreads();
+    if (warp == kMmaWarp) tmem_dealloc(tmem_base, 512);
+  }
 }
 
 // ---------------------------------------------------------------------------
@@ -905,7 +961,8 @@ inline int create_tc(nfb_handle* h) {
   if (cudaMalloc(&h->d_aux, (size_t)auxf * sizeof(float)) != cudaSuccess) return fail("cudaMalloc aux failed");
   if (cudaMemset(h->d_aux, 0, (size_t)auxf * sizeof(float)) != cudaSuccess) return fail("cudaMemset failed");
   if (cudaFuncSetAttribute(field_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes) != cudaSuccess ||
-      cudaFuncSetAttribute(field_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes) != cudaSuccess)
+      cudaFuncSetAttribute(field_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes) != cudaSuccess ||
+      cudaFuncSetAttribute(field_tc_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes) != cudaSuccess)
     return fail("cannot reserve %d bytes of shared memory for the tcgen05 kernel", kTcSmemBytes);
   return 0;
 }
@@ -974,6 +1031,33 @@ inline int run_field_tc(nfb_handle* h, int level, const FieldArgs& a, cudaStream
   const int grid = (int)std::min<long long>(pairs, h->sm_count);
   // NFB_TC_EPI_WARPS=8|16 selects the epilogue width (default: see kDefaultEpiWarps).
   static const int epi_warps = getenv("NFB_TC_EPI_WARPS") ? atoi(getenv("NFB_TC_EPI_WARPS")) : kDefaultEpiWarps;
+  // NFB_TC_PAIR=1 selects the CTA-pair (cta_group::2) variant: experimental, read per launch.
+  const char* pair_env = getenv("NFB_TC_PAIR");
+  if (pair_env && atoi(pair_env) == 1) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(h->sm_count & ~1)); cfg.blockDim = dim3(kTcThreads);
+    cfg.dynamicSmemBytes = kTcSmemBytes; cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    // persistent kernel: no more clusters than can be co-resident (GPCs with an odd
+    // number of free SMs leave one SM without a partner)
+    static int max_clusters = -1;
+    if (max_clusters < 0) {
+      int n = 0;
+      if (cudaOccupancyMaxActiveClusters(&n, field_tc_kernel<1, true>, &cfg) != cudaSuccess || n < 1)
+        return fail("cudaOccupancyMaxActiveClusters failed for the CTA-pair kernel: %s", cudaGetErrorString(cudaGetLastError()));
+      max_clusters = n;
+    }
+    const int grid2 = 2 * (int)std::min<long long>((pairs + 1) / 2, max_clusters);
+    cfg.gridDim = dim3((unsigned)grid2);
+    cudaError_t le = cudaLaunchKernelEx(&cfg, field_tc_kernel<1, true>, h->tcprog[level], h->tcbias[level], a,
+                                        (const uint8_t*)h->d_wpack, (const float*)h->d_aux, (int)pairs);
+    if (le != cudaSuccess) return fail("field_tc_kernel (CTA pair) launch failed: %s", cudaGetErrorString(le));
+    h->launches++;
+    return 0;
+  }
   if (epi_warps == 16)
     field_tc_kernel<2><<<grid, kTcThreads16, kTcSmemBytes, s>>>(h->tcprog[level], h->tcbias[level], a, h->d_wpack, h->d_aux, (int)pairs);
   else

@@ -388,6 +388,108 @@ __device__ __forceinline__ uint32_t issue_half1(uint32_t d1, uint64_t ad1, uint6
   return out;
 }
 
+// ---- CTA-pair (cta_group::2) variants of the two issue blocks -------------------
+// Same structure as issue_half0 / issue_half1; the MMAs are M = 256 across the two
+// CTAs of the cluster and every commit is multicast to the barrier at the same
+// shared-memory offset in both CTAs.
+__device__ __forceinline__ void issue_half0_pair(uint32_t d0, uint64_t ad0, uint64_t bd, uint32_t idesc,
+                                                 uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred pacc, pt;\n\t"
+      ".reg .b64 a1, a2, a3, b1, b2, b3;\n\t"
+      "tcgen05.fence::after_thread_sync;\n\t"
+      "setp.ne.b32 pacc, %4, 0;\n\t"
+      "setp.eq.b32 pt, 0, 0;\n\t"
+      "add.u64 a1, %1, 2;\n\t add.u64 a2, %1, 4;\n\t add.u64 a3, %1, 6;\n\t"
+      "add.u64 b1, %2, 2;\n\t add.u64 b2, %2, 4;\n\t add.u64 b3, %2, 6;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, pacc;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], a1, b1, %3, pt;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], a2, b2, %3, pt;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], a3, b3, %3, pt;\n\t"
+      "}"
+      ::"r"(d0), "l"(ad0), "l"(bd), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t issue_half1_pair(uint32_t d1, uint64_t ad1, uint64_t bd, uint32_t idesc,
+                                                     uint32_t accumulate, uint32_t bar_empty,
+                                                     uint32_t bar_xfree, uint32_t bar_acc, uint32_t probe_w,
+                                                     uint32_t par_w, uint32_t probe_x0, uint32_t probe_x1,
+                                                     uint32_t probe_x2, uint32_t par_x) {
+  uint32_t out;
+  const uint16_t both = 0x3;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred pacc, pt, pw, px0, px1, px2, pd0, pd1, pd2, pcx, pca;\n\t"
+      ".reg .b64 a1, a2, a3, b1, b2, b3;\n\t"
+      ".reg .b32 t0, t1, t2;\n\t"
+      "setp.ne.b32 pacc, %5, 0;\n\t"
+      "setp.eq.b32 pt, 0, 0;\n\t"
+      "setp.ne.b32 pd0, %11, 0;\n\t"
+      "setp.ne.b32 pd1, %12, 0;\n\t"
+      "setp.ne.b32 pd2, %13, 0;\n\t"
+      "setp.ne.b32 pcx, %7, 0;\n\t"
+      "setp.ne.b32 pca, %8, 0;\n\t"
+      "setp.eq.b32 px0, 1, 0;\n\t"
+      "setp.eq.b32 px1, 1, 0;\n\t"
+      "setp.eq.b32 px2, 1, 0;\n\t"
+      "add.u64 a1, %2, 2;\n\t add.u64 a2, %2, 4;\n\t add.u64 a3, %2, 6;\n\t"
+      "add.u64 b1, %3, 2;\n\t add.u64 b2, %3, 4;\n\t add.u64 b3, %3, 6;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%1], %2, %3, %4, pacc;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%1], a1, b1, %4, pt;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 pw, [%9], %10;\n\t"
+      "@pd0 mbarrier.test_wait.parity.shared::cta.b64 px0, [%11], %14;\n\t"
+      "@pd1 mbarrier.test_wait.parity.shared::cta.b64 px1, [%12], %14;\n\t"
+      "@pd2 mbarrier.test_wait.parity.shared::cta.b64 px2, [%13], %14;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%1], a2, b2, %4, pt;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%1], a3, b3, %4, pt;\n\t"
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%6], %15;\n\t"
+      "@pcx tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%7], %15;\n\t"
+      "@pca tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%8], %15;\n\t"
+      "selp.u32 %0, 1, 0, pw;\n\t"
+      "selp.u32 t0, 2, 0, px0;\n\t"
+      "selp.u32 t1, 4, 0, px1;\n\t"
+      "selp.u32 t2, 8, 0, px2;\n\t"
+      "or.b32 %0, %0, t0;\n\t"
+      "or.b32 %0, %0, t1;\n\t"
+      "or.b32 %0, %0, t2;\n\t"
+      "}"
+      : "=r"(out)
+      : "r"(d1), "l"(ad1), "l"(bd), "r"(idesc), "r"(accumulate), "r"(bar_empty), "r"(bar_xfree),
+        "r"(bar_acc), "r"(probe_w), "r"(par_w), "r"(probe_x0), "r"(probe_x1), "r"(probe_x2),
+        "r"(par_x), "h"(both)
+      : "memory");
+  return out;
+}
+
+// Cluster helpers for the CTA-pair kernels.
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// Arrives on the mbarrier at the same shared-memory offset in CTA `cta` of the cluster.
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t cta) {
+  uint32_t raddr;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(smem_u32(bar)), "r"(cta));
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(raddr) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc2(uint32_t* smem_slot, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                   smem_u32(smem_slot)),
+               "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols)
+               : "memory");
+}
+
 // ---- bf16 helpers ---------------------------------------------------------------
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);

@@ -197,14 +197,18 @@ def run_reference(args):
   sec = sum(times) / len(times)
   value = n * EVALS_PER_RAY / sec
   line = {
-      'impl': 'reference', 'metric': 'ray-samples/sec (coarse+fine)',
+      # same metric / unit / workload as the b200 arm (host-timed: there is no device)
+      'impl': 'reference', 'metric': 'ray-samples/sec (coarse+fine, device-timed)',
       'value': value, 'unit': 'ray-samples/s', 'n_gpus': args.gpus,
       'steps': args.steps, 'warmup': min(args.warmup, 1),
       'ms_per_step': sec * 1e3, 'higher_is_better': True, 'scaling': 'weak',
       'vs_baseline': None, 'dtype': 'fp32', 'data': 'synthetic',
-      'config': {'workload': f'north-star synthetic, quarterhd dims, '
-                             f'({NC}+{NF}) samples; bounded sample of {n} rays '
-                             'per step on the host CPU'},
+      'config': {'workload': f'north-star synthetic: 65536 rays/GPU x ({NC}+{NF}) samples = '
+                             f'{EVALS_PER_RAY} ray-samples/ray, gpu_quarterhd.gin model dims, SE(3) '
+                             f'warp on, deterministic sampling, trained-like random weights; each '
+                             f'step a bounded sample of {n} rays of it on the host CPU',
+                 'rays_per_step': n, 'precision': 'fp32',
+                 'timing': 'host wall clock around the reference algorithm (oracle port)'},
       'cpu_baseline': {'value': value, 'unit': 'ray-samples/s',
                        'cores': threads, 'kind': 'port',
                        'sample': f'{n} rays per step; restated reference on '

@@ -25,123 +25,70 @@ def _stream(device):
   return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
+_FIELDS = ('orientation', 'position', 'focal_length', 'principal_point', 'skew', 'pixel_aspect_ratio',
+           'radial_distortion', 'tangential_distortion', 'image_size')
+
+
 class Camera:
-  """Class to handle camera geometry (field names of camera.py:110-137)."""
+  """Camera geometry with the field names, JSON layout and derived properties of
+  nerfies.camera.Camera (camera.py:108-223); the ray math itself runs on the GPU."""
 
   def __init__(self, orientation, position, focal_length, principal_point, image_size, skew=0.0,
                pixel_aspect_ratio=1.0, radial_distortion=None, tangential_distortion=None,
                dtype=np.float32):
     if dtype != np.float32:
       raise ValueError('nerfies_b200.Camera computes in float32 like the reference default')
-    if radial_distortion is None:
-      radial_distortion = np.array([0.0, 0.0, 0.0], dtype)
-    if tangential_distortion is None:
-      tangential_distortion = np.array([0.0, 0.0], dtype)
-    self.orientation = np.array(orientation, dtype)
-    self.position = np.array(position, dtype)
-    self.focal_length = np.array(focal_length, dtype)
-    self.principal_point = np.array(principal_point, dtype)
-    self.skew = np.array(skew, dtype)
-    self.pixel_aspect_ratio = np.array(pixel_aspect_ratio, dtype)
-    self.radial_distortion = np.array(radial_distortion, dtype)
-    self.tangential_distortion = np.array(tangential_distortion, dtype)
-    self.image_size = np.array(image_size, np.uint32)
+    values = dict(orientation=orientation, position=position, focal_length=focal_length,
+                  principal_point=principal_point, skew=skew, pixel_aspect_ratio=pixel_aspect_ratio,
+                  radial_distortion=np.zeros(3) if radial_distortion is None else radial_distortion,
+                  tangential_distortion=np.zeros(2) if tangential_distortion is None else tangential_distortion)
+    for name, value in values.items():
+      setattr(self, name, np.array(value, np.float32))
+    self.image_size = np.array(image_size, np.uint32)   # (width, height), camera.py:136
     self.dtype = dtype
     if self.orientation.shape != (3, 3) or self.position.shape != (3,):
       raise ValueError('orientation must be (3,3) and position (3,)')
 
-  # ---- JSON (camera.py:139-180) ----
+  # ---- JSON (same keys as camera.py:139-180, including the legacy 'tangential') ----
   @classmethod
   def from_json(cls, path):
-    """Loads a JSON camera into memory."""
     with open(str(path), 'r') as fp:
-      camera_json = json.load(fp)
-    if 'tangential' in camera_json:          # old camera JSON (camera.py:147-148)
-      camera_json['tangential_distortion'] = camera_json['tangential']
-    return cls(
-        orientation=np.asarray(camera_json['orientation']),
-        position=np.asarray(camera_json['position']),
-        focal_length=camera_json['focal_length'],
-        principal_point=np.asarray(camera_json['principal_point']),
-        skew=camera_json['skew'],
-        pixel_aspect_ratio=camera_json['pixel_aspect_ratio'],
-        radial_distortion=np.asarray(camera_json['radial_distortion']),
-        tangential_distortion=np.asarray(camera_json['tangential_distortion']),
-        image_size=np.asarray(camera_json['image_size']))
-
-  def to_json(self):
-    return {k: (v.tolist() if hasattr(v, 'tolist') else v) for k, v in self.get_parameters().items()}
+      blob = json.load(fp)
+    if 'tangential' in blob:
+      blob['tangential_distortion'] = blob['tangential']
+    return cls(**{name: np.asarray(blob[name]) for name in _FIELDS})
 
   def get_parameters(self):
-    return {
-        'orientation': self.orientation, 'position': self.position,
-        'focal_length': self.focal_length, 'principal_point': self.principal_point,
-        'skew': self.skew, 'pixel_aspect_ratio': self.pixel_aspect_ratio,
-        'radial_distortion': self.radial_distortion,
-        'tangential_distortion': self.tangential_distortion, 'image_size': self.image_size,
-    }
+    return {name: getattr(self, name) for name in _FIELDS}
 
-  # ---- properties (camera.py:182-223) ----
-  @property
-  def scale_factor_x(self):
-    return self.focal_length
+  def to_json(self):
+    return {name: np.asarray(value).tolist() for name, value in self.get_parameters().items()}
 
-  @property
-  def scale_factor_y(self):
-    return self.focal_length * self.pixel_aspect_ratio
-
-  @property
-  def principal_point_x(self):
-    return self.principal_point[0]
-
-  @property
-  def principal_point_y(self):
-    return self.principal_point[1]
-
-  @property
-  def has_tangential_distortion(self):
-    return any(self.tangential_distortion != 0.0)
-
-  @property
-  def has_radial_distortion(self):
-    return any(self.radial_distortion != 0.0)
-
-  @property
-  def image_size_y(self):
-    return self.image_size[1]
-
-  @property
-  def image_size_x(self):
-    return self.image_size[0]
-
-  @property
-  def image_shape(self):
-    return int(self.image_size_y), int(self.image_size_x)
-
-  @property
-  def optical_axis(self):
-    return self.orientation[2, :]
-
-  @property
-  def translation(self):
-    return -np.matmul(self.orientation, self.position)
+  # ---- derived quantities (names of camera.py:182-223) ----
+  scale_factor_x = property(lambda self: self.focal_length)
+  scale_factor_y = property(lambda self: self.focal_length * self.pixel_aspect_ratio)
+  principal_point_x = property(lambda self: self.principal_point[0])
+  principal_point_y = property(lambda self: self.principal_point[1])
+  has_tangential_distortion = property(lambda self: bool(np.any(self.tangential_distortion != 0.0)))
+  has_radial_distortion = property(lambda self: bool(np.any(self.radial_distortion != 0.0)))
+  image_size_x = property(lambda self: self.image_size[0])
+  image_size_y = property(lambda self: self.image_size[1])
+  image_shape = property(lambda self: (int(self.image_size[1]), int(self.image_size[0])))
+  optical_axis = property(lambda self: self.orientation[2, :])
+  translation = property(lambda self: -np.matmul(self.orientation, self.position))
 
   def copy(self):
     return copy.deepcopy(self)
 
   def scale(self, scale):
-    """Scales the camera (camera.py:323-341)."""
+    """A camera for the image resized by `scale` (camera.py:323-341)."""
     if scale <= 0:
       raise ValueError('scale needs to be positive.')
-    return Camera(
-        orientation=self.orientation.copy(), position=self.position.copy(),
-        focal_length=self.focal_length * scale,
-        principal_point=self.principal_point.copy() * scale, skew=self.skew,
-        pixel_aspect_ratio=self.pixel_aspect_ratio,
-        radial_distortion=self.radial_distortion.copy(),
-        tangential_distortion=self.tangential_distortion.copy(),
-        image_size=np.array((int(round(self.image_size[0] * scale)),
-                             int(round(self.image_size[1] * scale)))))
+    params = {k: np.copy(v) for k, v in self.get_parameters().items()}
+    params['focal_length'] = self.focal_length * scale
+    params['principal_point'] = self.principal_point * scale
+    params['image_size'] = np.array([int(round(float(n) * scale)) for n in self.image_size])
+    return Camera(**params)
 
   # ---- the C-ABI view ----
   def _struct(self):

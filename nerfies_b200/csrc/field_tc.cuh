@@ -255,7 +255,14 @@ __device__ __forceinline__ void cond_to_block(uint8_t* block, int r, const float
 // ready" events: the follower's otherwise idle issuer warp walks the same unit
 // table, waits on its local barriers and forwards each event with one remote
 // mbarrier arrive (the leader's full / x_ready barriers count one extra arrival).
-template <int kH, bool kPair = false>
+// kPairMode 1 (NFB_TC_PAIR=1): as described - validated bit-identical on the GPU.
+// kPairMode 2 (NFB_TC_PAIR=2, written after the round's GPU budget was spent, NOT
+// yet run): the "activations ready" events skip the relay hop - the epilogue
+// threads of BOTH CTAs arrive on the leader's x_ready barriers directly (remote
+// release arrive; count 2 x kEpiThreads) - and the relay warp forwards only the
+// "weights landed" events, with a relaxed remote arrive (no data passed through
+// the relaying thread), so it is never blocked behind an activation wait.
+template <int kH, int kPairMode = 0>
 __global__ void __launch_bounds__(32 * (8 * kH + 4), 1)
 field_tc_kernel(const __grid_constant__ TcProgram prog, const __grid_constant__ TcBias biasp,
                 const FieldArgs args, const uint8_t* __restrict__ wpack,
@@ -275,6 +282,8 @@ field_tc_kernel(const __grid_constant__ TcProgram prog, const __grid_constant__ 
   TcBars* bars = reinterpret_cast<TcBars*>(reinterpret_cast<uint8_t*>(alpha_s) + kAlphaBytes);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  constexpr bool kPair = kPairMode != 0;
+  constexpr bool kDirectX = kPairMode == 2;                  // epilogues arrive on the leader's x_ready directly
   const uint32_t rank = kPair ? cluster_ctarank() : 0u;      // 0 = leader (issues the MMAs)
   const bool leader = rank == 0;
   if (tid == kMmaWarp * 32) {
@@ -282,7 +291,8 @@ field_tc_kernel(const __grid_constant__ TcProgram prog, const __grid_constant__ 
     for (int i = 0; i < kStages; ++i) { mbar_init(&bars->full[i], 1 + relay); mbar_init(&bars->empty[i], 1); }
     mbar_init(&bars->acc_ready[0], 1); mbar_init(&bars->acc_ready[1], 1);
     mbar_init(&bars->x_free, 1);
-    for (int k = 0; k < 3; ++k) mbar_init(&bars->x_ready[k], kEpiThreads + relay);
+    for (int k = 0; k < 3; ++k)
+      mbar_init(&bars->x_ready[k], (kDirectX && leader) ? 2 * kEpiThreads : kEpiThreads + relay);
     mbar_init(&bars->never, 1);
     fence_barrier_init();
   }
@@ -359,12 +369,17 @@ field_tc_kernel(const __grid_constant__ TcProgram prog, const __grid_constant__ 
       for (int pair = blockIdx.x; pair < pair_lim; pair += gridDim.x) {
         for (int u = u_begin; u < u_end; ++u) {
           const uint32_t flags = prog.units[u].flags;
-          // in the order the leader's issuer consumes them
-          if (flags & kUWaitX0) { mbar_wait(&bars->x_ready[0], xr & 1, dead); mbar_arrive_remote(&bars->x_ready[0], 0); }
-          if (flags & kUWaitX1) { mbar_wait(&bars->x_ready[1], xr & 1, dead); mbar_arrive_remote(&bars->x_ready[1], 0); }
-          if (flags & kUWaitX2) { mbar_wait(&bars->x_ready[2], xr & 1, dead); mbar_arrive_remote(&bars->x_ready[2], 0); }
-          mbar_wait(&bars->full[sg], wph, dead);
-          mbar_arrive_remote(&bars->full[sg], 0);
+          if constexpr (!kDirectX) {
+            // in the order the leader's issuer consumes them
+            if (flags & kUWaitX0) { mbar_wait(&bars->x_ready[0], xr & 1, dead); mbar_arrive_remote(&bars->x_ready[0], 0); }
+            if (flags & kUWaitX1) { mbar_wait(&bars->x_ready[1], xr & 1, dead); mbar_arrive_remote(&bars->x_ready[1], 0); }
+            if (flags & kUWaitX2) { mbar_wait(&bars->x_ready[2], xr & 1, dead); mbar_arrive_remote(&bars->x_ready[2], 0); }
+            mbar_wait(&bars->full[sg], wph, dead);
+            mbar_arrive_remote(&bars->full[sg], 0);
+          } else {
+            mbar_wait(&bars->full[sg], wph, dead);
+            mbar_arrive_remote_relaxed(&bars->full[sg], 0);
+          }
           sg = (sg + 1) & (kStages - 1);
           wph ^= (sg == 0 ? 1u : 0u);
           xr += (flags & kUStepEnd) ? 1u : 0u;
@@ -485,13 +500,19 @@ field_tc_kernel(const __grid_constant__ TcProgram prog, const __grid_constant__ 
     RowState row;
     const int S = args.samples_per_ray;
     auto epi_sync = [&]() { asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory"); };
+    // "this thread's part of the activations is in shared memory" (the async-proxy
+    // fence precedes every call); mode 2 of the CTA pair signals the leader directly.
+    auto x_arrive = [&](uint64_t* bar) {
+      if constexpr (kDirectX) mbar_arrive_remote(bar, 0);
+      else mbar_arrive(bar);
+    };
 
     auto arrive_both = [&]() {
       fence_proxy_async();
       tc_fence_before();
-      mbar_arrive(&bars->x_ready[0]);
-      mbar_arrive(&bars->x_ready[1]);
-      mbar_arrive(&bars->x_ready[2]);
+      x_arrive(&bars->x_ready[0]);
+      x_arrive(&bars->x_ready[1]);
+      x_arrive(&bars->x_ready[2]);
     };
     // Sample point of this thread's row for tile pair `pair`, and the first
     // input block (model_utils.py:72-73; warping.py:325-326 / models.py:270).
@@ -622,7 +643,7 @@ field_tc_kernel(const __grid_constant__ TcProgram prog, const __grid_constant__ 
             cond_to_block(ins, r, args.cond + row.ray * prog.cond_stride + prog.G, prog.rc, cb, ce);
           fence_proxy_async();
           tc_fence_before();
-          mbar_arrive(&bars->x_ready[0]);
+          x_arrive(&bars->x_ready[0]);
           tr.ev(si, 3);
           // ---- chunk 1: every MMA of the layer is complete, store directly ----
           mbar_wait(&bars->acc_ready[1], n_acc1++ & 1, dead);
@@ -650,7 +671,7 @@ field_tc_kernel(const __grid_constant__ TcProgram prog, const __grid_constant__ 
             sts_piece(xs_a0, 160, pk);
             fence_proxy_async();
             tc_fence_before();
-            mbar_arrive(&bars->x_ready[1]);
+            x_arrive(&bars->x_ready[1]);
             tmem_ld_wait();
             epi_piece(vc, bias4 + 48, relu, adot, aw + 192, row.alpha, pk);
             sts_piece(xs_a0, 192, pk);
@@ -695,7 +716,7 @@ field_tc_kernel(const __grid_constant__ TcProgram prog, const __grid_constant__ 
                 if (kH == 1 && pp == 0 && np == 4) {
                   fence_proxy_async();
                   tc_fence_before();
-                  mbar_arrive(&bars->x_ready[1]);
+                  x_arrive(&bars->x_ready[1]);
                 }
               }
             }
@@ -708,8 +729,8 @@ field_tc_kernel(const __grid_constant__ TcProgram prog, const __grid_constant__ 
           }
           fence_proxy_async();
           tc_fence_before();
-          if (!(kH == 1 && np == 4) || (args.debug & 1)) mbar_arrive(&bars->x_ready[1]);
-          mbar_arrive(&bars->x_ready[2]);
+          if (!(kH == 1 && np == 4) || (args.debug & 1)) x_arrive(&bars->x_ready[1]);
+          x_arrive(&bars->x_ready[2]);
           tr.ev(si, 5);
         } else {
           // ---- heads: N = 16 accumulator columns, one chunk (both threads of a
@@ -962,7 +983,8 @@ inline int create_tc(nfb_handle* h) {
   if (cudaMemset(h->d_aux, 0, (size_t)auxf * sizeof(float)) != cudaSuccess) return fail("cudaMemset failed");
   if (cudaFuncSetAttribute(field_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes) != cudaSuccess ||
       cudaFuncSetAttribute(field_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes) != cudaSuccess ||
-      cudaFuncSetAttribute(field_tc_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes) != cudaSuccess)
+      cudaFuncSetAttribute(field_tc_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes) != cudaSuccess ||
+      cudaFuncSetAttribute(field_tc_kernel<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes) != cudaSuccess)
     return fail("cannot reserve %d bytes of shared memory for the tcgen05 kernel", kTcSmemBytes);
   return 0;
 }
@@ -1033,7 +1055,8 @@ inline int run_field_tc(nfb_handle* h, int level, const FieldArgs& a, cudaStream
   static const int epi_warps = getenv("NFB_TC_EPI_WARPS") ? atoi(getenv("NFB_TC_EPI_WARPS")) : kDefaultEpiWarps;
   // NFB_TC_PAIR=1 selects the CTA-pair (cta_group::2) variant: experimental, read per launch.
   const char* pair_env = getenv("NFB_TC_PAIR");
-  if (pair_env && atoi(pair_env) == 1) {
+  const int pair_mode = pair_env ? atoi(pair_env) : 0;
+  if (pair_mode == 1 || pair_mode == 2) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(h->sm_count & ~1)); cfg.blockDim = dim3(kTcThreads);
     cfg.dynamicSmemBytes = kTcSmemBytes; cfg.stream = s;
@@ -1046,13 +1069,14 @@ inline int run_field_tc(nfb_handle* h, int level, const FieldArgs& a, cudaStream
     static int max_clusters = -1;
     if (max_clusters < 0) {
       int n = 0;
-      if (cudaOccupancyMaxActiveClusters(&n, field_tc_kernel<1, true>, &cfg) != cudaSuccess || n < 1)
+      if (cudaOccupancyMaxActiveClusters(&n, field_tc_kernel<1, 1>, &cfg) != cudaSuccess || n < 1)
         return fail("cudaOccupancyMaxActiveClusters failed for the CTA-pair kernel: %s", cudaGetErrorString(cudaGetLastError()));
       max_clusters = n;
     }
     const int grid2 = 2 * (int)std::min<long long>((pairs + 1) / 2, max_clusters);
     cfg.gridDim = dim3((unsigned)grid2);
-    cudaError_t le = cudaLaunchKernelEx(&cfg, field_tc_kernel<1, true>, h->tcprog[level], h->tcbias[level], a,
+    auto kern = pair_mode == 2 ? field_tc_kernel<1, 2> : field_tc_kernel<1, 1>;
+    cudaError_t le = cudaLaunchKernelEx(&cfg, kern, h->tcprog[level], h->tcbias[level], a,
                                         (const uint8_t*)h->d_wpack, (const float*)h->d_aux, (int)pairs);
     if (le != cudaSuccess) return fail("field_tc_kernel (CTA pair) launch failed: %s", cudaGetErrorString(le));
     h->launches++;

@@ -256,8 +256,8 @@ __device__ __forceinline__ void cond_to_block(uint8_t* block, int r, const float
 // table, waits on its local barriers and forwards each event with one remote
 // mbarrier arrive (the leader's full / x_ready barriers count one extra arrival).
 // kPairMode 1 (NFB_TC_PAIR=1): as described - validated bit-identical on the GPU.
-// kPairMode 2 (NFB_TC_PAIR=2, written after the round's GPU budget was spent, NOT
-// yet run): the "activations ready" events skip the relay hop - the epilogue
+// kPairMode 2 (NFB_TC_PAIR=2; checked bit-identical once, tools/check_pair_mode.py,
+// not yet tuned or measured on the bench workload): the "activations ready" events skip the relay hop - the epilogue
 // threads of BOTH CTAs arrive on the leader's x_ready barriers directly (remote
 // release arrive; count 2 x kEpiThreads) - and the relay warp forwards only the
 // "weights landed" events, with a relaxed remote arrive (no data passed through

@@ -1,20 +1,28 @@
 """Benchmark of the render hot path (NerfModel.__call__) on B200.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--precision P]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--precision P] [--workload W]
   python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
   python bench.py --impl reference ...      # the reference's CPU path (oracle port)
 
-Metric (BASELINE.json): ray-samples/sec, coarse+fine, device-timed.  One
-ray-sample = one (warp MLP + NeRF MLP) point evaluation; a ray costs
+Metric (BASELINE.json): ray-samples/sec, coarse+fine, device-timed; PSNR vs ref.
+One ray-sample = one (warp MLP + NeRF MLP) point evaluation; a ray costs
 Nc + (Nc + Nf) of them.  A step = one forward of the whole
-pipeline over one batch of synthetic rays.  Workload: the north-star synthetic
-(65,536 rays x (128+128) samples, gpu_quarterhd.gin model dimensions) per GPU;
-rays shard across GPUs with no data-path collective (weak scaling).
+pipeline over one batch of synthetic rays.  Default workload: the north-star
+synthetic (65,536 rays x (128+128) samples, gpu_quarterhd.gin model dimensions)
+per GPU; rays shard across GPUs with no data-path collective (weak scaling).
+
+The headline (`value`, `e2e`, `roofline`) is measured in the PARITY-HOLDING
+tensor-core mode (precision fp16x3: 1e-4 per stage against the reference's fp32
+arithmetic); the bf16 mode's throughput and its measured error are reported next
+to it under `also`.  After the timed region the line's `parity` object compares a
+sample of the rays that were just timed with the oracle (max-rel errors, PSNR); a
+run whose errors exceed the mode's stated bound exits non-zero.
 
 One JSON line is printed by rank 0 (see the task contract for the keys).
 """
 import argparse
 import json
+import math
 import os
 import statistics
 import subprocess
@@ -26,11 +34,46 @@ REPO = os.path.dirname(os.path.abspath(__file__))
 if REPO not in sys.path:
   sys.path.insert(0, REPO)
 
-FLOP_PER_RAY_SAMPLE = 1370112   # 2 x (97,792 + 587,264) MAC
-NC, NF = 128, 128
-EVALS_PER_RAY = NC + NC + NF
 NEAR, FAR = 0.02, 0.83
 N_IDS = 200
+
+# SURVEY.md §8(d) workloads: model dimensions of the gin files, forward FLOP per
+# ray-sample = 2 x (warp MLP + NeRF MLP MACs); padding / emulation passes not counted.
+WORKLOADS = {
+    'northstar': dict(
+        rays=65536, nc=128, nf=128, fp=8, fw=8, app=True, cam=False, flop=1370112,
+        desc='north-star synthetic: {B} rays/GPU x (128+128) samples = 384 ray-samples/ray, '
+             'gpu_quarterhd.gin model dims'),
+    'quarterhd-train': dict(
+        rays=6144, nc=128, nf=128, fp=8, fw=8, app=True, cam=False, flop=1370112,
+        desc='gpu_quarterhd.gin training batch: {B} rays x (128+128) samples'),
+    'vrig-train': dict(
+        rays=6144, nc=128, nf=128, fp=8, fw=6, app=False, cam=True, flop=1364480,
+        desc='gpu_vrig_paper.gin batch: {B} rays x (128+128) samples, num_warp_freqs=6, '
+             'camera metadata (rgb condition 29)'),
+    'fullhd-train': dict(
+        rays=4096, nc=256, nf=256, fp=10, fw=8, app=True, cam=False, flop=1382400,
+        desc='gpu_fullhd.gin training batch: {B} rays x (256+256) samples, num_nerf_point_freqs=10'),
+    'fullhd-65536': dict(
+        rays=65536, nc=256, nf=256, fp=10, fw=8, app=True, cam=False, flop=1382400,
+        desc='gpu_fullhd.gin model dims at {B} rays x (256+256) samples'),
+}
+
+# Stated parity bounds per mode, metric |a-b| / (|b| + 1e-2) (absolute below 1e-2).
+#   coarse      : coarse level, well conditioned              (the 1e-4 gate)
+#   fine_oracle_z: fine level evaluated on the oracle's z     (the 1e-4 gate)
+#   e2e         : fine level end to end; inverse-CDF resampling amplifies fp32
+#                 round-off in empty space, stated 2e-3
+PARITY_BOUNDS = {
+    'fp32': dict(coarse=1e-4, fine_oracle_z=1e-4, e2e=2e-3, psnr_db=70.0),
+    'fp16x3': dict(coarse=1e-4, fine_oracle_z=1e-4, e2e=2e-3, psnr_db=70.0),
+    'bf16': dict(coarse=8e-2, fine_oracle_z=8e-2, e2e=1.5e-1, psnr_db=35.0),
+}
+DTYPE_NAMES = {
+    'fp32': 'fp32',
+    'bf16': 'bf16',
+    'fp16x3': 'fp16x3 (fp32 emulated on tcgen05: 3 fp16 MMA chains, fp32 accumulate)',
+}
 
 
 def parse_args():
@@ -39,46 +82,86 @@ def parse_args():
   ap.add_argument('--steps', type=int, default=5)
   ap.add_argument('--warmup', type=int, default=3)
   ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
-  ap.add_argument('--rays', type=int, default=65536, help='rays per GPU per step')
-  ap.add_argument('--precision', default=None,
-                  choices=[None, 'fp32', 'bf16', 'bf16x3'])
+  ap.add_argument('--workload', default='northstar', choices=sorted(WORKLOADS))
+  ap.add_argument('--rays', type=int, default=None, help='rays per GPU per step (default: the workload\'s)')
+  ap.add_argument('--precision', default=None, choices=[None, 'fp32', 'bf16', 'fp16x3'],
+                  help='headline mode (default: fp16x3, the parity-holding tensor-core mode)')
+  ap.add_argument('--scaling', default='weak', choices=['weak', 'strong'],
+                  help='weak: --rays per GPU; strong: --rays in total, split over the ranks')
+  ap.add_argument('--no-also', action='store_true', help='skip the secondary modes / strong-scaling extras')
   ap.add_argument('--no-cpu-baseline', action='store_true')
+  ap.add_argument('--no-parity', action='store_true')
   ap.add_argument('--cpu-seconds', type=float, default=15.0)
   return ap.parse_args()
 
 
-def oracle_spec():
+def oracle_spec(wl):
   from oracle import nerfies_oracle as O
   return O.OracleSpec(
-      num_coarse_samples=NC, num_fine_samples=NF, near=NEAR, far=FAR,
-      num_nerf_point_freqs=8, sigma_activation='softplus', use_warp=True,
-      warp_field_type='se3', use_appearance_metadata=True,
-      num_warp_embeddings=N_IDS, num_appearance_embeddings=N_IDS)
+      num_coarse_samples=wl['nc'], num_fine_samples=wl['nf'], near=NEAR, far=FAR,
+      num_nerf_point_freqs=wl['fp'], num_warp_freqs=wl['fw'], sigma_activation='softplus',
+      use_warp=True, warp_field_type='se3', use_appearance_metadata=wl['app'],
+      use_camera_metadata=wl['cam'], num_warp_embeddings=N_IDS,
+      num_appearance_embeddings=N_IDS if wl['app'] else 1,
+      num_camera_embeddings=2 if wl['cam'] else 1)
 
 
-def model_config():
+def model_config(wl):
   import nerfies_b200 as nb
-  # gpu_quarterhd.gin (+ warp_defaults.gin, defaults.gin) model fields; the
-  # deterministic path (eval.py:239).
+  # gpu_*.gin (+ warp_defaults.gin, defaults.gin) model fields; the deterministic
+  # path (eval.py:239).
   return nb.configs.ModelConfig(
       use_stratified_sampling=False, use_viewdirs=True, use_warp=True,
-      warp_field_type='se3', num_warp_freqs=8, num_warp_features=8,
-      use_appearance_metadata=True, sigma_activation='softplus',
-      num_nerf_point_freqs=8, nerf_trunk_width=256, nerf_trunk_depth=8,
-      num_coarse_samples=NC, num_fine_samples=NF)
+      warp_field_type='se3', num_warp_freqs=wl['fw'], num_warp_features=8,
+      use_appearance_metadata=wl['app'], use_camera_metadata=wl['cam'],
+      camera_metadata_dims=2, sigma_activation='softplus',
+      num_nerf_point_freqs=wl['fp'], nerf_trunk_width=256, nerf_trunk_depth=8,
+      num_coarse_samples=wl['nc'], num_fine_samples=wl['nf'])
 
 
-def synthetic_rays(num_rays, seed):
+def trained_like(params, scale=3.0, bias_std=0.1, seed=1):
+  """"Trained-like" random weights: hidden kernels x1.3, heads xscale,
+  the density head x4*scale, small non-zero warp heads, N(0, bias_std) biases - so
+  that sigma / alpha / the resampled PDF are non-degenerate.  The same recipe (and
+  the same torch CPU generator stream) as the oracle's test helper, restated here so
+  that the product arm does not import oracle/ for its inputs."""
+  import torch
+  gen = torch.Generator().manual_seed(seed)
+
+  def rec(t, path):
+    if isinstance(t, dict):
+      return {k: rec(v, path + (k,)) for k, v in t.items()}
+    if 'warp_field' in path and path[-2] == 'logit':
+      if path[-1] == 'kernel':
+        return (torch.rand(t.shape, generator=gen) * 2 - 1) * 2e-3
+      return (torch.rand(t.shape, generator=gen) * 2 - 1) * 1e-2
+    if path[-1] == 'kernel':
+      if path[-2] == 'logit' and 'MLP_2' in path:
+        return t * (4.0 * scale)
+      if path[-2] == 'logit':
+        return t * scale
+      return t * 1.3
+    if path[-1] == 'bias':
+      return torch.randn(t.shape, generator=gen) * bias_std
+    return t
+
+  return rec(params, ())
+
+
+def synthetic_rays(num_rays, seed, wl):
   """SURVEY.md §8(d) synthetic inputs, float32, seeded."""
   import torch
   g = torch.Generator().manual_seed(seed)
   origins = torch.rand(num_rays, 3, generator=g) - 0.5
   d = torch.randn(num_rays, 3, generator=g)
   directions = d / torch.linalg.norm(d, dim=-1, keepdim=True)
-  md = {'warp': torch.randint(0, N_IDS, (num_rays, 1), generator=g,
-                              dtype=torch.int32),
-        'appearance': torch.randint(0, N_IDS, (num_rays, 1), generator=g,
-                                    dtype=torch.int32)}
+  md = {'warp': torch.randint(0, N_IDS, (num_rays, 1), generator=g, dtype=torch.int32),
+        'appearance': torch.randint(0, N_IDS, (num_rays, 1), generator=g, dtype=torch.int32),
+        'camera': torch.randint(0, 2, (num_rays, 1), generator=g, dtype=torch.int32)}
+  if not wl['app']:
+    md.pop('appearance')
+  if not wl['cam']:
+    md.pop('camera')
   return {'origins': origins, 'directions': directions, 'metadata': md}
 
 
@@ -136,11 +219,14 @@ class ClockSampler:
             'samples': len(sm)}
 
 
-def time_oracle(num_rays, threads, seed=0):
+# ----------------------------------------------------------------------------
+# CPU legs: the reference's algorithm on the host (oracle port).
+# ----------------------------------------------------------------------------
+def time_oracle(num_rays, threads, wl, seed=0):
   """Seconds for one oracle forward of `num_rays` rays (torch CPU fp32)."""
   import torch
   from oracle import nerfies_oracle as O
-  spec = oracle_spec()
+  spec = oracle_spec(wl)
   torch.set_num_threads(threads)
   params = O.make_trained_like(O.init_params(spec, seed), seed=seed + 1)
   rays = O.synthetic_rays(num_rays, spec, seed=seed + 2)
@@ -151,36 +237,42 @@ def time_oracle(num_rays, threads, seed=0):
       sub = {'origins': rays['origins'][s:s + chunk],
              'directions': rays['directions'][s:s + chunk],
              'metadata': {k: v[s:s + chunk] for k, v in rays['metadata'].items()}}
-      O.render_forward(params, spec, sub, warp_alpha=8.0)
+      O.render_forward(params, spec, sub, warp_alpha=float(wl['fw']))
   return time.perf_counter() - t0
 
 
-def best_thread_count():
+def best_thread_count(wl):
   """torch's intra-op pool does not scale to every core on large hosts (128
   threads on the GPU box is ~30x slower than 8-32): probe a few counts on a small
   sample and keep the fastest.  Returns (threads, rays_per_second)."""
   cores = os.cpu_count() or 1
   cands = sorted({c for c in (cores, 64, 32, 16, 8) if c <= cores})
-  time_oracle(128, cands[0])                     # warm-up (thread pools, MKL)
+  time_oracle(128, cands[0], wl)                 # warm-up (thread pools, MKL)
   best = None
   for c in cands:
-    t = time_oracle(128, c)
+    t = time_oracle(128, c, wl)
     if best is None or t < best[1]:
       best = (c, t)
   return best[0], 128 / best[1]
 
 
-def cpu_baseline(budget_s):
+def cpu_baseline(budget_s, wl):
   """The reference's algorithm on the host cores (oracle port; the JAX original
   cannot run in this image), on a bounded sample of the same workload."""
-  threads, rate = best_thread_count()
+  threads, rate = best_thread_count(wl)
   n = int(min(16384, max(256, rate * budget_s)) // 256 * 256)
-  t = time_oracle(n, threads)
-  return {'value': n * EVALS_PER_RAY / t, 'unit': 'ray-samples/s',
+  t = time_oracle(n, threads, wl)
+  evals = 2 * wl['nc'] + wl['nf']
+  return {'value': n * evals / t, 'unit': 'ray-samples/s',
           'cores': threads, 'kind': 'port',
-          'sample': f'{n} rays x ({NC}+{NF}) samples, quarterhd dims, '
+          'sample': f'{n} rays x ({wl["nc"]}+{wl["nf"]}) samples of the workload, '
                     f'torch-CPU fp32 oracle, {t:.1f} s; {threads} of '
                     f'{os.cpu_count()} host threads (fastest of a probe)'}
+
+
+def workload_text(wl, B):
+  return (wl['desc'].format(B=B) + ', SE(3) warp on, deterministic sampling, '
+          'trained-like random weights')
 
 
 def run_reference(args):
@@ -189,24 +281,25 @@ def run_reference(args):
   rank = int(os.environ.get('RANK', '0'))
   if rank != 0:
     return
-  threads, rate = best_thread_count()
+  wl = WORKLOADS[args.workload]
+  B = args.rays or wl['rays']
+  evals = 2 * wl['nc'] + wl['nf']
+  threads, rate = best_thread_count(wl)
   n = int(min(8192, max(256, rate * 8.0)) // 256 * 256)   # ~8 s per step
   for _ in range(min(args.warmup, 1)):
-    time_oracle(n, threads)
-  times = [time_oracle(n, threads) for _ in range(args.steps)]
+    time_oracle(n, threads, wl)
+  times = [time_oracle(n, threads, wl) for _ in range(args.steps)]
   sec = sum(times) / len(times)
-  value = n * EVALS_PER_RAY / sec
+  value = n * evals / sec
   line = {
       # same metric / unit / workload as the b200 arm (host-timed: there is no device)
       'impl': 'reference', 'metric': 'ray-samples/sec (coarse+fine, device-timed)',
       'value': value, 'unit': 'ray-samples/s', 'n_gpus': args.gpus,
       'steps': args.steps, 'warmup': min(args.warmup, 1),
-      'ms_per_step': sec * 1e3, 'higher_is_better': True, 'scaling': 'weak',
+      'ms_per_step': sec * 1e3, 'higher_is_better': True, 'scaling': args.scaling,
       'vs_baseline': None, 'dtype': 'fp32', 'data': 'synthetic',
-      'config': {'workload': f'north-star synthetic: 65536 rays/GPU x ({NC}+{NF}) samples = '
-                             f'{EVALS_PER_RAY} ray-samples/ray, gpu_quarterhd.gin model dims, SE(3) '
-                             f'warp on, deterministic sampling, trained-like random weights; each '
-                             f'step a bounded sample of {n} rays of it on the host CPU',
+      'config': {'workload': workload_text(wl, B) + f'; each step a bounded sample of {n} rays '
+                             'of it on the host CPU',
                  'rays_per_step': n, 'precision': 'fp32',
                  'timing': 'host wall clock around the reference algorithm (oracle port)'},
       'cpu_baseline': {'value': value, 'unit': 'ray-samples/s',
@@ -220,42 +313,95 @@ def run_reference(args):
   emit(line)
 
 
-def run_b200(args):
+# ----------------------------------------------------------------------------
+# The b200 arm
+# ----------------------------------------------------------------------------
+def rel_err(a, b, floor=1e-2):
+  a, b = a.double(), b.double()
+  return float(((a - b).abs() / (b.abs() + floor)).max())
+
+
+def psnr_db(a, b):
+  """utils.compute_psnr (utils.py:94-103): -10 log10(mse)."""
+  mse = float(((a.double() - b.double())**2).mean())
+  return -10.0 * math.log10(max(mse, 1e-20))
+
+
+def parity_check(model, variables, params_cpu, rays_host, out, wl, precision, n_sample=256):
+  """Compares a sample of the rays that were just timed with the oracle
+  (BASELINE.json: "PSNR vs ref"): the step's own outputs for the coarse level and
+  end to end, plus the fine level re-evaluated on the oracle's z (the
+  well-conditioned per-stage check)."""
+  import torch
+  from oracle import nerfies_oracle as O   # the checker, outside every timed region
+  from nerfies_b200.models import _prep_f32, _prep_ids, _ptr, _stream
+  from nerfies_b200 import _lib
+  spec = oracle_spec(wl)
+  B = rays_host['origins'].shape[0]
+  n = min(n_sample, B)
+  idx = torch.linspace(0, B - 1, n).round().long()
+  sub = {'origins': rays_host['origins'][idx], 'directions': rays_host['directions'][idx],
+         'metadata': {k: v[idx] for k, v in rays_host['metadata'].items()}}
+  alpha = float(wl['fw'])
+  torch.set_num_threads(min(16, os.cpu_count() or 1))
+  with torch.no_grad():
+    ref = O.render_forward(params_cpu, spec, sub, warp_alpha=alpha, return_points=True)
+  dev = model.device
+  got = {lv: {k: out[lv][k][idx.to(dev)].cpu() for k in ('rgb', 'depth', 'acc')}
+         for lv in ('coarse', 'fine')}
+  res = {'rays': n, 'metric': 'max |a-b| / (|b| + 1e-2) vs the fp32 oracle (oracle/nerfies_oracle.py)'}
+  res['coarse'] = {f'max_rel_{k}': rel_err(got['coarse'][k], ref['coarse'][k]) for k in ('rgb', 'depth', 'acc')}
+  res['e2e'] = {f'max_rel_{k}': rel_err(got['fine'][k], ref['fine'][k]) for k in ('rgb', 'depth', 'acc')}
+  res['e2e']['psnr_db'] = psnr_db(got['fine']['rgb'], ref['fine']['rgb'])
+  # fine level on the oracle's z through nfb_render_samples
+  hd = model.handle(B)
+  z = ref['fine']['z_vals'].contiguous()
+  S = z.shape[1]
+  o = _prep_f32(sub['origins'], dev)
+  d = _prep_f32(sub['directions'], dev)
+  ids = [_prep_ids(sub['metadata'].get(k), dev) for k in ('warp', 'appearance', 'camera')]
+  zc = _prep_f32(z, dev)
+  buf = torch.empty(n, 6, device=dev)
+  _lib.check(hd.lib.nfb_render_samples(
+      hd.h, 1, n, S, _ptr(zc), _ptr(o), _ptr(d), None, _ptr(ids[0]), _ptr(ids[1]), _ptr(ids[2]),
+      alpha, 0, _ptr(buf), None, None, None, _stream()))
+  torch.cuda.synchronize()
+  buf = buf.cpu()
+  fz = {'rgb': buf[:, :3], 'depth': buf[:, 3], 'acc': buf[:, 5]}
+  res['fine_oracle_z'] = {f'max_rel_{k}': rel_err(fz[k], ref['fine'][k]) for k in ('rgb', 'depth', 'acc')}
+  res['fine_oracle_z']['psnr_db'] = psnr_db(fz['rgb'], ref['fine']['rgb'])
+  bounds = PARITY_BOUNDS[precision]
+  ok = all(max(v for k, v in res[s].items() if k.startswith('max_rel')) < bounds[s]
+           for s in ('coarse', 'fine_oracle_z', 'e2e'))
+  ok = ok and res['e2e']['psnr_db'] > bounds['psnr_db']
+  res['bounds'] = bounds
+  res['ok'] = bool(ok)
+  return res
+
+
+def measure(precision, wl, B, args, ctx, want_parity):
+  """Times `args.steps` forwards of B rays per rank in one precision mode."""
   import torch
   import torch.distributed as dist
   import nerfies_b200 as nb
-
-  world = int(os.environ.get('WORLD_SIZE', '1'))
-  rank = int(os.environ.get('RANK', '0'))
-  local_rank = int(os.environ.get('LOCAL_RANK', '0'))
-  if world > 1:
-    os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
-    dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
-  if args.gpus != world and rank == 0 and world > 1:
-    print(f'warning: --gpus {args.gpus} but WORLD_SIZE={world}', file=sys.stderr)
-  torch.cuda.set_device(local_rank)
-  dev = torch.device('cuda', local_rank)
-
-  precision = args.precision or default_precision()
-  B = args.rays
-  model, params = nb.construct_nerf(0, model_config(), B, range(N_IDS), [0],
+  dev, world, rank, local_rank = ctx['dev'], ctx['world'], ctx['rank'], ctx['local_rank']
+  evals = 2 * wl['nc'] + wl['nf']
+  model, params = nb.construct_nerf(0, model_config(wl), B, range(N_IDS), range(2),
                                     range(N_IDS), NEAR, FAR,
                                     precision=precision, device=dev)
-  # "trained-like" weights: non-degenerate densities so the
-  # resampled PDF and the composite do real work.
-  from oracle import nerfies_oracle as O  # weights recipe only (not timed)
   cpu = lambda t: ({k: cpu(v) for k, v in t.items()} if isinstance(t, dict)
                    else t.cpu())
   gpu = lambda t: ({k: gpu(v) for k, v in t.items()} if isinstance(t, dict)
                    else t.to(dev))
-  params = gpu(O.make_trained_like(cpu(params), seed=1))
-  rays_host = synthetic_rays(B, seed=1000 + rank)   # each rank its own rays
+  params_cpu = trained_like(cpu(params), seed=1)
+  params = gpu(params_cpu)
+  rays_host = synthetic_rays(B, 1000 + rank, wl)   # each rank its own rays
   rays = {'origins': rays_host['origins'].to(dev),
           'directions': rays_host['directions'].to(dev),
           'metadata': {k: v.to(dev) for k, v in rays_host['metadata'].items()}}
   variables = {'params': params}
-  warp_extra = {'alpha': 8.0, 'time_alpha': 0.0}
-  flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+  warp_extra = {'alpha': float(wl['fw']), 'time_alpha': 0.0}
+  flush = ctx['flush']
 
   def step():
     return model.apply(variables, rays, warp_extra=warp_extra)
@@ -265,7 +411,7 @@ def run_b200(args):
       dist.barrier()
     torch.cuda.synchronize()
 
-  for _ in range(args.warmup):
+  for _ in range(max(args.warmup, 3)):
     out = step()
   hd = model.handle(B)
   _ = hd.lib.nfb_set_profiling(hd.h, 1)
@@ -296,27 +442,118 @@ def run_b200(args):
   if world > 1:
     dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
   ms_per_step = float(total_ms) / args.steps
-  value = world * B * EVALS_PER_RAY / (ms_per_step * 1e-3)
+  res = {
+      'precision': precision, 'ms_per_step': ms_per_step,
+      'value': world * B * evals / (ms_per_step * 1e-3),
+      'launches': int(launches), 'clocks': clocks, 'wall': wall,
+      'field_ms': (statistics.mean(m[0] for m in field_ms), statistics.mean(m[1] for m in field_ms)),
+  }
+  if want_parity and rank == 0:
+    res['parity'] = parity_check(model, variables, params_cpu, rays_host, out, wl, precision)
+  res['model'], res['variables'], res['rays_host'], res['warp_extra'] = model, variables, rays_host, warp_extra
+  return res
+
+
+def roofline(res, wl, B, peaks, precision):
+  fc, ff = res['field_ms']
+  fine_flop = B * (wl['nc'] + wl['nf']) * wl['flop']
+  achieved = fine_flop / (ff * 1e-3) / 1e12
+  # a step is tens of milliseconds between flushes and syncs: the burst cuBLAS peak
+  # is the denominator; the sustained one is quoted beside it.
+  peak = peaks.get('bf16_tflops') or peaks.get('bf16_tflops_sustained')
+  peak_src = 'measured (MEASURED_PEAKS.json, burst bf16 cuBLAS 8192^3)'
+  if not peak:
+    peak, peak_src = 1590.0, 'fallback (B200_PROFILING.md)'
+  traffic = None
+  try:
+    with open(os.path.join(REPO, 'profiles', 'traffic.json')) as f:
+      traffic = json.load(f).get(precision, {}).get('field_fine_dram_bytes')
+  except (OSError, ValueError):
+    pass
+  notes = {
+      'fp32': 'fp32 mode runs on the FFMA pipe; the fraction is still quoted against the bf16 '
+              'tensor peak the north-star names',
+      'fp16x3': 'ALGORITHMIC FLOPs only: the three fp16 MMA chains that emulate fp32 execute 3x '
+                'this many tensor FLOPs (no credit taken); tensor-pipe busy fraction = 3 x frac',
+      'bf16': '',
+  }
+  r = {
+      'bound': 'tensor', 'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s',
+      'frac': achieved / peak, 'traffic': traffic,
+      'kernel': f'field kernel, fine level ({B * (wl["nc"] + wl["nf"])} rows x {wl["flop"]} FLOP)',
+      'kernel_ms': ff, 'coarse_kernel_ms': fc,
+      'share_of_step': (fc + ff) / res['ms_per_step'],
+      'peak_source': peak_src, 'note': notes[precision],
+  }
+  if peaks.get('bf16_tflops_sustained'):
+    r['frac_of_sustained_peak'] = achieved / peaks['bf16_tflops_sustained']
+  if precision == 'fp16x3':
+    r['tensor_pipe_frac_executed'] = 3 * achieved / peak
+  return r
+
+
+def run_b200(args):
+  import torch
+  import torch.distributed as dist
+
+  world = int(os.environ.get('WORLD_SIZE', '1'))
+  rank = int(os.environ.get('RANK', '0'))
+  local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+  if world > 1:
+    os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+    dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+  if args.gpus != world and rank == 0 and world > 1:
+    print(f'warning: --gpus {args.gpus} but WORLD_SIZE={world}', file=sys.stderr)
+  torch.cuda.set_device(local_rank)
+  dev = torch.device('cuda', local_rank)
+  wl = WORKLOADS[args.workload]
+  precision = args.precision or 'fp16x3'
+  total_rays = args.rays or wl['rays']
+  B = total_rays if args.scaling == 'weak' else max(1, total_rays // world)
+  evals = 2 * wl['nc'] + wl['nf']
+  ctx = {'dev': dev, 'world': world, 'rank': rank, 'local_rank': local_rank,
+         'flush': torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)}
+
+  def barrier():
+    if world > 1:
+      dist.barrier()
+    torch.cuda.synchronize()
+
+  main = measure(precision, wl, B, args, ctx, want_parity=not args.no_parity)
 
   # End to end through the C ABI's host entry point: host buffers in, host
   # buffers out, H2D + D2H inside the timed region.
+  model, variables, rays_host = main['model'], main['variables'], main['rays_host']
   host_rays = {'origins': rays_host['origins'].numpy(),
                'directions': rays_host['directions'].numpy(),
                'metadata': {k: v.numpy() for k, v in rays_host['metadata'].items()}}
-  model.apply_host(variables, host_rays, warp_extra=warp_extra)   # warm-up
+  model.apply_host(variables, host_rays, warp_extra=main['warp_extra'])   # warm-up
   e2e_steps = max(2, min(args.steps, 5))
   barrier()
   t0 = time.perf_counter()
   for _ in range(e2e_steps):
-    host_out = model.apply_host(variables, host_rays, warp_extra=warp_extra)
+    model.apply_host(variables, host_rays, warp_extra=main['warp_extra'])
   barrier()
   e2e_s = torch.tensor([(time.perf_counter() - t0) / e2e_steps], device=dev,
                        dtype=torch.float64)
   if world > 1:
     dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
-  e2e_value = world * B * EVALS_PER_RAY / float(e2e_s)
-  h2d = B * (12 + 12 + 4 + 4)          # origins, directions, warp id, appearance id
-  d2h = B * 2 * 6 * 4                  # (B,6) per level
+  e2e_value = world * B * evals / float(e2e_s)
+  n_id_arrays = 1 + int(wl['app']) + int(wl['cam'])
+  h2d = B * (12 + 12 + 4 * n_id_arrays)   # origins, directions, metadata ids
+  d2h = B * 2 * 6 * 4                     # (B,6) per level
+
+  also = {}
+  if not args.no_also:
+    for other in ('bf16',):
+      if other == precision:
+        continue
+      r = measure(other, wl, B, args, ctx, want_parity=not args.no_parity)
+      also[other] = r
+    if world > 1 and args.scaling == 'weak':
+      # strong scaling beside the weak headline: the same TOTAL batch split over the ranks
+      r = measure(precision, wl, max(1, total_rays // world), args, ctx, want_parity=False)
+      also['strong'] = r
 
   if rank != 0:
     if world > 1:
@@ -329,73 +566,59 @@ def run_b200(args):
       peaks = json.load(f)
   except OSError:
     pass
-  # The field kernel runs for ~all of a multi-hundred-ms step: sustained peak.
-  peak = peaks.get('bf16_tflops_sustained') or peaks.get('bf16_tflops')
-  peak_src = 'measured (MEASURED_PEAKS.json, sustained bf16 cuBLAS)'
-  if not peak:
-    peak, peak_src = 1590.0, 'fallback (B200_PROFILING.md)'
-  fc = statistics.mean(m[0] for m in field_ms)
-  ff = statistics.mean(m[1] for m in field_ms)
-  # dominant kernel = the fine-level field launch (2/3 of the ray-samples).
-  fine_flop = B * (NC + NF) * FLOP_PER_RAY_SAMPLE
-  achieved = fine_flop / (ff * 1e-3) / 1e12
-  traffic = None
-  try:
-    with open(os.path.join(REPO, 'profiles', 'traffic.json')) as f:
-      traffic = json.load(f).get(precision, {}).get('field_fine_dram_bytes')
-  except (OSError, ValueError):
-    pass
   line = {
       'metric': 'ray-samples/sec (coarse+fine, device-timed)',
-      'value': value, 'unit': 'ray-samples/s', 'n_gpus': world,
-      'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_per_step,
-      'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-      'dtype': {'fp32': 'fp32', 'bf16': 'bf16', 'bf16x3': 'bf16x3 (fp32-emulating)'}[precision],
+      'value': main['value'], 'unit': 'ray-samples/s', 'n_gpus': world,
+      'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': main['ms_per_step'],
+      'higher_is_better': True, 'scaling': args.scaling, 'vs_baseline': None,
+      'dtype': DTYPE_NAMES[precision],
       'data': 'synthetic',
       'config': {
-          'workload': f'north-star synthetic: {B} rays/GPU x ({NC}+{NF}) samples '
-                      f'= {EVALS_PER_RAY} ray-samples/ray, gpu_quarterhd.gin model '
-                      'dims, SE(3) warp on, deterministic sampling, trained-like '
-                      'random weights',
+          'workload': workload_text(wl, B),
+          'workload_name': args.workload,
           'rays_per_gpu': B, 'precision': precision,
           'parallelism': f'ray sharding x{world}, no data-path collective',
-          'l2': 'L2 flushed (256 MiB memset) between timed iterations; the '
-                'per-step working set (268 MB of per-sample outputs) also '
-                'exceeds L2',
-          'timing': 'per-step CUDA events on the launch stream, summed, max '
-                    'over ranks',
+          'l2': 'L2 flushed (256 MiB memset) between timed iterations; the per-step working set '
+                '(per-sample outputs) also exceeds L2 at the default batch',
+          'timing': 'per-step CUDA events on the launch stream, summed, max over ranks',
       },
-      'clocks': clocks,
+      'clocks': main['clocks'],
       'e2e': {'value': e2e_value, 'unit': 'ray-samples/s',
               'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
               'api': 'NerfModel.apply_host -> nfb_render_forward_host (host '
                      'buffers, pinned staging, H2D+D2H timed)'},
-      'gpu_launches': int(launches),
-      'roofline': {
-          'bound': 'tensor', 'achieved': achieved, 'peak': peak,
-          'unit': 'TFLOP/s', 'frac': achieved / peak, 'traffic': traffic,
-          'kernel': 'field kernel, fine level '
-                    f'({B * (NC + NF)} rows x {FLOP_PER_RAY_SAMPLE} FLOP)',
-          'kernel_ms': ff, 'coarse_kernel_ms': fc,
-          'share_of_step': (fc + ff) / ms_per_step,
-          'peak_source': peak_src,
-          'note': ('fp32 parity mode runs on the FFMA pipe; the fraction is '
-                   'still quoted against the bf16 tensor peak the north-star names'
-                   if precision == 'fp32' else ''),
-      },
-      'wall_s_timed_region': wall,
+      'gpu_launches': main['launches'],
+      'roofline': roofline(main, wl, B, peaks, precision),
+      'wall_s_timed_region': main['wall'],
   }
+  if 'parity' in main:
+    line['parity'] = main['parity']
+  if also:
+    line['also'] = {}
+    for name, r in also.items():
+      if name == 'strong':
+        b2 = max(1, total_rays // world)
+        line['also']['strong_scaling'] = {
+            'precision': precision, 'total_rays': b2 * world, 'rays_per_gpu': b2,
+            'value': r['value'], 'ms_per_step': r['ms_per_step'],
+            'note': 'same workload with the TOTAL batch fixed and split over the ranks; '
+                    'efficiency = value / (N x the N=1 value of the default line)'}
+      else:
+        line['also'][name] = {
+            'value': r['value'], 'ms_per_step': r['ms_per_step'],
+            'dtype': DTYPE_NAMES[name], 'roofline_frac': roofline(r, wl, B, peaks, name)['frac'],
+            'fine_kernel_ms': r['field_ms'][1], 'clocks': r['clocks'],
+            'parity': r.get('parity')}
   if not args.no_cpu_baseline:
-    line['cpu_baseline'] = cpu_baseline(args.cpu_seconds)
+    line['cpu_baseline'] = cpu_baseline(args.cpu_seconds, wl)
+  bad = 'parity' in line and not line['parity']['ok']
+  if bad:
+    line['invalid'] = 'parity check failed: errors exceed the stated bound of this precision mode'
   emit(line)
   if world > 1:
     dist.destroy_process_group()
-
-
-def default_precision():
-  """The fastest mode the built library contains."""
-  return 'bf16' if os.path.exists(os.path.join(
-      REPO, 'nerfies_b200', 'csrc', 'field_tc.cuh')) else 'fp32'
+  if bad:
+    sys.exit(3)
 
 
 _SAVED_STDOUT = None

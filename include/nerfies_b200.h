@@ -41,9 +41,14 @@ enum nfb_activation {
 enum nfb_warp_type { NFB_WARP_NONE = 0, NFB_WARP_TRANSLATION = 1, NFB_WARP_SE3 = 2 };
 /* Arithmetic of the MLP GEMMs.  Everything else is always fp32. */
 enum nfb_precision {
-  NFB_PREC_FP32 = 0,     /* fp32 FFMA on CUDA cores: the parity mode            */
-  NFB_PREC_BF16 = 1,     /* bf16 operands, fp32 accumulate, tcgen05 tensor cores */
-  NFB_PREC_BF16X3 = 2    /* fp32 emulated as 3 bf16 MMAs (hi/lo split), tcgen05  */
+  NFB_PREC_FP32 = 0,     /* fp32 FFMA on CUDA cores: general (any width / activation / condition) */
+  NFB_PREC_BF16 = 1,     /* bf16 operands, fp32 accumulate, tcgen05 tensor cores: fastest, ~1e-2  */
+  NFB_PREC_FP16X3 = 2    /* fp32 emulated on tcgen05 by three fp16 MMA chains into one fp32
+                          * accumulator (x_hi W_hi + x_lo W_hi + x_hi W_lo, hi = fp16(v),
+                          * lo = fp16(v - hi): 22 significant bits per operand): the
+                          * tensor-core mode that holds the 1e-4 parity gate.  Activations
+                          * beyond fp16's range (|v| > 65504) saturate.  (Round 1 reserved this
+                          * value as "bf16x3"; a bf16 split leaves 2^-17 per operand, not enough.) */
 };
 
 /* Mirrors the NerfModel attributes that shape the forward pass
@@ -196,6 +201,13 @@ int nfb_pixels_to_rays(const nfb_camera* cam, const float* pixels, long long n,
  * zero it first).  NULL disables tracing.  Only builds compiled with -DNFB_TRACE
  * carry the tracer; others return -1 for a non-NULL buffer. */
 int nfb_set_trace(nfb_handle* h, long long* buffer, int capacity);
+
+/* Test hook for the abort path described in the conventions above: while enabled,
+ * the MMA issuer of the bf16 tcgen05 kernel first waits on an mbarrier that never
+ * completes, so the launch must time out, drain and raise the abort flag
+ * (tests/test_edge_cases_gpu.py).  The process cannot run further tensor-core
+ * launches afterwards.  No reference analogue. */
+int nfb_debug_provoke_timeout(nfb_handle* h, int enabled);
 
 /* Hardware self-test of the tcgen05 building blocks (UMMA descriptors, 128-byte
  * swizzle, TMEM, bulk-copy ring): C[128,N] = bf16(A[128,K]) x bf16(W[K,N]), fp32

@@ -18,12 +18,13 @@ SYMBOLS = [
     'nfb_warp_forward', 'nfb_kernel_launches', 'nfb_last_error', 'nfb_version',
     'nfb_set_profiling', 'nfb_field_time_ms', 'nfb_selftest_gemm', 'nfb_set_trace', 'nfb_selftest_microbench',
     'nfb_camera_rays', 'nfb_pixels_to_rays', 'nfb_selftest_gemm2',
+    'nfb_debug_provoke_timeout',
 ]
 
 ACTIVATIONS = {'none': 0, 'relu': 1, 'elu': 2, 'leaky_relu': 3, 'tanh': 4,
                'sigmoid': 5, 'softplus': 6}
 WARP_TYPES = {None: 0, 'none': 0, 'translation': 1, 'se3': 2}
-PRECISIONS = {'fp32': 0, 'bf16': 1, 'bf16x3': 2}
+PRECISIONS = {'fp32': 0, 'bf16': 1, 'fp16x3': 2}
 FLAG_COARSE_ONLY = 1
 FLAG_NO_WARP = 2
 FLAG_METADATA_ENCODED = 4
@@ -152,6 +153,8 @@ def load():
   lib.nfb_pixels_to_rays.restype = ci
   lib.nfb_selftest_gemm2.argtypes = [ci, ci, vp, vp, vp, ci, vp, vp]
   lib.nfb_selftest_gemm2.restype = ci
+  lib.nfb_debug_provoke_timeout.argtypes = [vp, ci]
+  lib.nfb_debug_provoke_timeout.restype = ci
   lib.nfb_last_error.argtypes = []
   lib.nfb_last_error.restype = ctypes.c_char_p
   lib.nfb_version.argtypes = []

@@ -802,13 +802,17 @@ field_tc_kernel(const __grid_constant__ TcProgram prog, const __grid_constant__ 
 // precision in nfb_api.cu) into TcPrograms, pack the weights, launch.
 // ---------------------------------------------------------------------------
 inline int tc_fail(const char* what) {
-  return fail("precision bf16 (tcgen05 path) does not support this model: %s; use precision fp32", what);
+  return fail("the tcgen05 paths (precision bf16 / fp16x3) do not support this model: %s; use precision fp32", what);
 }
 
 inline int build_tc_program(nfb_handle* h, int level, long long* wbytes, long long* aux_floats) {
   const FieldProgram& fp = h->prog[level];
   TcProgram& tp = h->tcprog[level];
   memset(&tp, 0, sizeof(tp));
+  // fp16x3 mode (field_tc3.cuh): same schedule, fp16 operands, every (chunk, K-block)
+  // has two weight units [W_hi | W_lo], and "sub-tile 1" of a unit is the lo image.
+  const bool x3 = h->cfg.precision == NFB_PREC_FP16X3;
+  const int wparts = x3 ? 2 : 1;
   tp.warp_type = fp.warp_type; tp.Fw = fp.Fw; tp.G = fp.G; tp.Fp = fp.Fp; tp.rc = fp.rc;
   tp.cond_stride = fp.cond_stride; tp.sigma_act = fp.sigma_act;
   if (fp.tc || fp.ac) return tc_fail("trunk/alpha conditions");
@@ -852,6 +856,7 @@ inline int build_tc_program(nfb_handle* h, int level, long long* wbytes, long lo
       nfb_handle::TcPackJob job;
       job.level = level; job.step = tp.n_steps; job.chunk = c;
       job.simt_w_off = st.w_off; job.ld = st.npad; job.n = st.n; job.n0 = c * t.chunk_n;
+      job.k_total = st.k_x + st.k_in;
       job.k_map.assign((size_t)t.nkb * kBlockK, -1);
       for (int kb = 0; kb < t.nkb; ++kb)
         for (int j = 0; j < kBlockK; ++j) {
@@ -861,9 +866,9 @@ inline int build_tc_program(nfb_handle* h, int level, long long* wbytes, long lo
           job.k_map[(size_t)kb * kBlockK + j] = srck;
         }
       h->tc_jobs.push_back(job);
-      *wbytes += (long long)t.nkb * t.chunk_n * kRowBytes;
+      *wbytes += (long long)wparts * t.nkb * t.chunk_n * kRowBytes;
     }
-    tp.units_per_pair += t.n_chunks * t.nkb;
+    tp.units_per_pair += wparts * t.n_chunks * t.nkb;
     ++tp.n_steps;
     return 0;
   };
@@ -908,6 +913,7 @@ inline int build_tc_program(nfb_handle* h, int level, long long* wbytes, long lo
     }
   }
   if (!seen_alpha || !seen_bottleneck) return tc_fail("model without bottleneck/alpha head");
+  tp.scale_off = (int)*aux_floats; *aux_floats += kMaxTcSteps;
   // Flatten the issuer's schedule (see TcUnit).
   tp.n_units = 0;
   int prev_split = 99, prev_split2 = 99;
@@ -934,7 +940,7 @@ inline int build_tc_program(nfb_handle* h, int level, long long* wbytes, long lo
         const int a0 = (b < kSrcIn) ? b * kABlockBytes : kXBytes;
         const int a1 = (b < kSrcIn) ? (4 + b) * kABlockBytes : kXBytes + kABlockBytes;
         u.a0_lo = (uint32_t)(a0 >> 4); u.a1_lo = (uint32_t)(a1 >> 4);
-        u.dcol = (uint32_t)(c * t.chunk_n); u.idesc = make_idesc_bf16(kTileRows, t.chunk_n);
+        u.dcol = (uint32_t)(c * t.chunk_n); u.idesc = x3 ? make_idesc_f16(kTileRows, t.chunk_n) : make_idesc_bf16(kTileRows, t.chunk_n);
         u.step = (uint32_t)si;
         if (kb) u.flags |= kUAccum;
         if (!have1 && (c == 1 || kb >= kb_need)) { u.flags |= kUWaitX1; have1 = true; }
@@ -981,6 +987,7 @@ inline int create_tc(nfb_handle* h) {
   if (cudaMalloc(&h->d_wpack, (size_t)wbytes) != cudaSuccess) return fail("cudaMalloc wpack failed");
   if (cudaMalloc(&h->d_aux, (size_t)auxf * sizeof(float)) != cudaSuccess) return fail("cudaMalloc aux failed");
   if (cudaMemset(h->d_aux, 0, (size_t)auxf * sizeof(float)) != cudaSuccess) return fail("cudaMemset failed");
+  if (h->cfg.precision == NFB_PREC_FP16X3) return 0;     // tc3::create_x3 reserves that kernel's shared memory
   if (cudaFuncSetAttribute(field_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes) != cudaSuccess ||
       cudaFuncSetAttribute(field_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes) != cudaSuccess ||
       cudaFuncSetAttribute(field_tc_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes) != cudaSuccess ||
@@ -1015,11 +1022,29 @@ inline int pack_tc(nfb_handle* h, cudaStream_t s) {
   if (e == cudaSuccess) e = cudaStreamSynchronize(s);   // `all` is pageable and local
   if (e != cudaSuccess) { cudaFree(d_maps); return fail("k_map upload failed: %s", cudaGetErrorString(e)); }
   size_t map_off = 0;
+  const bool x3 = h->cfg.precision == NFB_PREC_FP16X3;
+  if (x3) {
+    // per-layer max |W| -> power-of-two scale (x3_weight_scale), computed on the device
+    for (int lv = 0; lv < 2; ++lv)
+      cudaMemsetAsync(h->d_aux + h->tcprog[lv].scale_off, 0, kMaxTcSteps * sizeof(float), s);
+    for (auto& j : h->tc_jobs) {
+      if (j.chunk != 0) continue;
+      const long long n = (long long)j.k_total * j.ld;
+      absmax_kernel<<<(unsigned)std::min<long long>((n + 255) / 256, 64), 256, 0, s>>>(
+          h->d_packed + j.simt_w_off, n, h->d_aux + h->tcprog[j.level].scale_off + j.step);
+      h->launches++;
+    }
+  }
   for (auto& j : h->tc_jobs) {
     const TcStep& t = h->tcprog[j.level].steps[j.step];
     const long long total = (long long)t.nkb * t.chunk_n * kBlockK;
-    uint8_t* dst = h->d_wpack + t.w_off + (size_t)j.chunk * t.nkb * t.chunk_n * kRowBytes;
+    uint8_t* dst = h->d_wpack + t.w_off + (size_t)(x3 ? 2 : 1) * j.chunk * t.nkb * t.chunk_n * kRowBytes;
     // source columns n0.. of the fp32 (K x npad) matrix: shift the base pointer.
+    if (x3)
+      pack_weight_x3_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(
+          h->d_packed + j.simt_w_off + j.n0, j.ld, d_maps + map_off, t.nkb, j.n - j.n0, t.chunk_n,
+          h->d_aux + h->tcprog[j.level].scale_off + j.step, dst);
+    else
     pack_weight_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(
         h->d_packed + j.simt_w_off + j.n0, j.ld, d_maps + map_off, t.nkb, j.n - j.n0, t.chunk_n,
         reinterpret_cast<__nv_bfloat16*>(dst));
@@ -1044,6 +1069,14 @@ inline int pack_tc(nfb_handle* h, cudaStream_t s) {
     memset(&h->tcbias[lv], 0, sizeof(TcBias));
     for (int si = 0; si < tp.n_steps; ++si)
       memcpy(reinterpret_cast<float*>(h->tcbias[lv].b4) + si * 256, h_aux.data() + tp.steps[si].b_off, 256 * sizeof(float));
+    if (x3) {
+      X3Consts& c = h->x3c[lv];
+      memset(&c, 0, sizeof(c));
+      memcpy(c.b4, h->tcbias[lv].b4, sizeof(c.b4));
+      memcpy(c.alpha4, h_aux.data() + tp.alpha_w_off, 256 * sizeof(float));
+      c.alpha_b = h_aux[tp.alpha_b_off];
+      for (int si = 0; si < tp.n_steps; ++si) c.inv_scale[si] = 1.f / x3_weight_scale(h_aux[tp.scale_off + si]);
+    }
   }
   return 0;
 }
@@ -1052,10 +1085,15 @@ inline int run_field_tc(nfb_handle* h, int level, const FieldArgs& a, cudaStream
   const long long pairs = (a.num_rows + kPairRows - 1) / kPairRows;
   const int grid = (int)std::min<long long>(pairs, h->sm_count);
   // NFB_TC_EPI_WARPS=8|16 selects the epilogue width (default: see kDefaultEpiWarps).
+  // Developer builds only (-DNFB_DEV_KNOBS, tools/build_variant.py): the release library reads
+  // no environment variables.  NFB_TC_PAIR=1|2 selects the CTA-pair (cta_group::2) variants.
+#ifdef NFB_DEV_KNOBS
   static const int epi_warps = getenv("NFB_TC_EPI_WARPS") ? atoi(getenv("NFB_TC_EPI_WARPS")) : kDefaultEpiWarps;
-  // NFB_TC_PAIR=1 selects the CTA-pair (cta_group::2) variant: experimental, read per launch.
   const char* pair_env = getenv("NFB_TC_PAIR");
   const int pair_mode = pair_env ? atoi(pair_env) : 0;
+#else
+  const int epi_warps = kDefaultEpiWarps, pair_mode = 0;
+#endif
   if (pair_mode == 1 || pair_mode == 2) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(h->sm_count & ~1)); cfg.blockDim = dim3(kTcThreads);

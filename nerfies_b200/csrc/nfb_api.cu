@@ -21,6 +21,7 @@
 #include "tc_selftest2.cuh"
 #ifdef NFB_WITH_TC
 #include "field_tc.cuh"
+#include "field_tc3.cuh"
 #endif
 
 namespace {
@@ -311,10 +312,14 @@ int run_field(nfb_handle* h, int level, long long rows, int S, const float* orig
   a.num_rows = rows; a.samples_per_ray = S; a.use_warp = use_warp; a.warp_only = warp_only;
   a.fast_encode = h->cfg.precision == NFB_PREC_BF16;
   a.trace = h->trace; a.trace_cap = h->trace_cap;
+#ifdef NFB_DEV_KNOBS
   {
+    // developer builds only: timing experiments whose results are garbage (see FieldArgs::debug)
     static const int dbg = getenv("NFB_DEBUG") ? atoi(getenv("NFB_DEBUG")) : 0;
     a.debug = dbg;
   }
+#endif
+  a.debug |= h->debug_bits;
   const bool prof = h->profiling && !warp_only;
   if (prof) NFB_CUDA(cudaEventRecord(h->ev[level][0], s));
   int rc;
@@ -324,7 +329,8 @@ int run_field(nfb_handle* h, int level, long long rows, int S, const float* orig
     rc = launch_check(h, "field_simt_kernel");
   } else {
 #ifdef NFB_WITH_TC
-    rc = nfb::tc::run_field_tc(h, level, a, s);
+    rc = h->cfg.precision == NFB_PREC_FP16X3 ? nfb::tc3::run_field_x3(h, level, a, s)
+                                             : nfb::tc::run_field_tc(h, level, a, s);
 #else
     rc = fail("precision %d needs the tcgen05 path, which this build does not contain", h->cfg.precision);
 #endif
@@ -461,6 +467,12 @@ int nfb_set_trace(nfb_handle* h, long long* buffer, int capacity) {
   return 0;
 }
 
+int nfb_debug_provoke_timeout(nfb_handle* h, int enabled) {
+  if (!h) return fail("null handle");
+  h->debug_bits = enabled ? 8 : 0;
+  return 0;
+}
+
 int nfb_set_profiling(nfb_handle* h, int enabled) {
   if (!h) return fail("null handle");
   if (enabled && !h->ev[0][0]) {
@@ -570,9 +582,7 @@ int nfb_create(const nfb_config* cfg, int max_rays, nfb_handle** out) {
   if (max_rays < 1) return fail("max_rays must be >= 1");
   if (cfg->num_coarse_samples < 2) return fail("num_coarse_samples must be >= 2");
   if (cfg->num_fine_samples < 0) return fail("num_fine_samples must be >= 0");
-  if (cfg->precision < NFB_PREC_FP32 || cfg->precision > NFB_PREC_BF16X3) return fail("bad precision");
-  if (cfg->precision == NFB_PREC_BF16X3)
-    return fail("precision bf16x3 (fp32 emulated by 3 bf16 MMAs) is reserved and not implemented in this build");
+  if (cfg->precision < NFB_PREC_FP32 || cfg->precision > NFB_PREC_FP16X3) return fail("bad precision");
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
     return fail("no CUDA device: nerfies_b200 has no CPU path");
@@ -613,6 +623,7 @@ int nfb_create(const nfb_config* cfg, int max_rays, nfb_handle** out) {
   cudaFuncSetAttribute(nfb::resample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
 #ifdef NFB_WITH_TC
   if (c.precision != NFB_PREC_FP32 && nfb::tc::create_tc(h)) return bail(-1);
+  if (c.precision == NFB_PREC_FP16X3 && nfb::tc3::create_x3(h)) return bail(-1);
 #endif
   *out = h;
   return 0;

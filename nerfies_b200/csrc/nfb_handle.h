@@ -86,15 +86,17 @@ struct nfb_handle {
   bool ev_valid[2] = {false, false};
   int cond_stride = 0;
   int sm_count = 148;
+  int debug_bits = 0;                 // FieldArgs::debug bits set through the test hook (abort-path test)
   long long* trace = nullptr;
   int trace_cap = 0;
   // tensor-core path (precision != fp32)
   nfb::tc::TcProgram tcprog[2];
   nfb::tc::TcBias tcbias[2];          // host copy of the per-step biases (kernel parameter)
+  nfb::tc::X3Consts x3c[2];           // fp16x3 mode: biases + alpha head (kernel parameter)
   unsigned char* d_wpack = nullptr;   // bf16 weight units, shared-memory image
   float* d_aux = nullptr;             // fp32 biases + alpha head
   long long wpack_bytes = 0, aux_floats = 0;
-  struct TcPackJob { int level, step, chunk; int simt_w_off, ld, n, n0; std::vector<int> k_map; };
+  struct TcPackJob { int level, step, chunk; int simt_w_off, ld, n, n0, k_total; std::vector<int> k_map; };
   std::vector<TcPackJob> tc_jobs;
   struct TcAuxJob { int src_off, count, stride, dst_off; };
   std::vector<TcAuxJob> tc_aux_jobs;

@@ -11,6 +11,7 @@
 // descriptor's start address.
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -230,6 +231,10 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
 __device__ __host__ __forceinline__ uint32_t make_idesc_bf16(int m, int n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) |
          ((uint32_t)(m >> 4) << 24);
+}
+// Same for fp16 x fp16 -> f32 (operand format 0).
+__device__ __host__ __forceinline__ uint32_t make_idesc_f16(int m, int n) {
+  return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 // D[tmem] (+)= A[smem] * B[smem]; issued by one thread.
 __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
@@ -551,6 +556,51 @@ __global__ void pack_weight_kernel(const float* __restrict__ w_packed_fp32, int 
   uint8_t* unit = reinterpret_cast<uint8_t*>(dst) + (size_t)kb * n_rows * kRowBytes;
   *reinterpret_cast<__nv_bfloat16*>(unit + swz_off(row, kk >> 3) + (kk & 7) * 2) =
       __float2bfloat16_rn(v);
+}
+
+// fp16x3 mode: every layer's weights are multiplied by a power of two s so that
+// max |W| s lies in [2, 4) before the fp16 hi/lo split, and the epilogue multiplies
+// the accumulator by 1/s (exact).  Without it small weights (the warp heads are
+// ~1e-3) push W_lo into fp16's subnormal range (absolute floor 2^-25) and the
+// split loses up to 10 bits; with it the split error is ~3e-7 of the layer output.
+__host__ __device__ __forceinline__ float x3_weight_scale(float absmax) {
+  if (!(absmax > 0.f) || !(absmax < 3.0e38f)) return 1.f;
+  int e = 0;
+  frexpf(absmax, &e);                      // absmax = f * 2^e, f in [0.5, 1)
+  e = 2 - e;
+  e = e < -100 ? -100 : (e > 100 ? 100 : e);
+  return ldexpf(1.f, e);
+}
+// max |w| over a float range (one slot per layer; non-negative floats order like uints).
+__global__ void absmax_kernel(const float* __restrict__ w, long long n, float* __restrict__ out) {
+  float m = 0.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    m = fmaxf(m, fabsf(w[i]));
+  for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<unsigned int*>(out), __float_as_uint(m));
+}
+
+// fp16x3 mode: fp32 (K x N, row-major, leading dimension ld) -> fp16 hi and lo units,
+// hi = rn(w), lo = rn(w - hi), interleaved per K-block: unit (kb, part) at
+// ((kb * 2 + part) * n_rows) rows x 128 bytes.
+__global__ void pack_weight_x3_kernel(const float* __restrict__ w, int ld, const int* __restrict__ k_map,
+                                      int nkb, int n, int n_rows, const float* __restrict__ absmax,
+                                      uint8_t* __restrict__ dst) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)nkb * n_rows * kBlockK;
+  if (idx >= total) return;
+  const int kk = (int)(idx % kBlockK);
+  const int row = (int)((idx / kBlockK) % n_rows);
+  const int kb = (int)(idx / ((long long)kBlockK * n_rows));
+  const int src_k = k_map[kb * kBlockK + kk];
+  float v = 0.f;
+  if (src_k >= 0 && row < n) v = w[(size_t)src_k * ld + row] * x3_weight_scale(*absmax);
+  const __half hi = __float2half_rn(v);
+  const __half lo = __float2half_rn(v - __half2float(hi));
+  uint8_t* unit = dst + (size_t)kb * 2 * n_rows * kRowBytes;
+  const uint32_t off = swz_off(row, kk >> 3) + (kk & 7) * 2;
+  *reinterpret_cast<__half*>(unit + off) = hi;
+  *reinterpret_cast<__half*>(unit + (size_t)n_rows * kRowBytes + off) = lo;
 }
 
 }  // namespace tc

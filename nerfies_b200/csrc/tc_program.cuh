@@ -58,6 +58,7 @@ struct TcProgram {
   TcUnit units[kMaxTcUnits];
   int warp_type, Fw, G, Fp, rc, cond_stride, sigma_act;
   int alpha_w_off, alpha_b_off;   // aux float offsets
+  int scale_off;                  // fp16x3: aux offset of the per-step max |W| (kMaxTcSteps floats)
   uint32_t units_per_pair;        // weight units streamed per tile pair
 };
 
@@ -66,6 +67,16 @@ struct TcProgram {
 // datapath instead of through the shared-memory pipe the MMAs are fed from.
 struct alignas(16) TcBias {
   float4 b4[kMaxTcSteps * 64];
+};
+
+// fp16x3 mode (field_tc3.cuh): per-step biases + the alpha head (Dense(1) on the
+// trunk output) in fp32, read from the kernel-parameter constant bank.
+struct alignas(16) X3Consts {
+  float4 b4[kMaxTcSteps * 64];
+  float4 alpha4[64];
+  float inv_scale[kMaxTcSteps];   // 1 / (power-of-two weight scale of the step), see x3_weight_scale()
+  float alpha_b;
+  float pad[3];
 };
 
 }  // namespace tc

@@ -138,7 +138,7 @@ def test_coarse_only_model_and_fullhd_dims_bf16():
 
 
 def test_protocol_error_aborts_instead_of_hanging():
-  """NFB_DEBUG=8 makes the MMA issuer wait on an mbarrier that never completes.
+  """nfb_debug_provoke_timeout makes the MMA issuer wait on an mbarrier that never completes.
 
   The kernel must drain (bounded spin -> host-visible abort flag -> every other
   waiter bails out) and the API must report the error, not hang the GPU."""
@@ -155,6 +155,8 @@ def test_protocol_error_aborts_instead_of_hanging():
               'directions': torch.nn.functional.normalize(torch.randn(256, 3, generator=g), dim=-1).cuda(),
               'metadata': {'warp': torch.zeros(256, 1, dtype=torch.int32).cuda(),
                            'appearance': torch.zeros(256, 1, dtype=torch.int32).cuda()}}
+      hd = model.handle(256)
+      hd.lib.nfb_debug_provoke_timeout(hd.h, 1)
       try:
         model.apply({'params': params}, rays, warp_extra={'alpha': 8.0})
         torch.cuda.synchronize()
@@ -163,7 +165,7 @@ def test_protocol_error_aborts_instead_of_hanging():
       except Exception as e:
         print('ERROR:', e)
   ''')
-  env = dict(os.environ, NFB_DEBUG='8')
+  env = dict(os.environ)
   root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
   out = subprocess.run([sys.executable, '-c', code], cwd=root, env=env, capture_output=True, text=True,
                        timeout=120)
@@ -174,7 +176,12 @@ def test_cta_pair_variant_is_bit_identical(monkeypatch):
   """NFB_TC_PAIR=1: the experimental cta_group::2 field kernel (two CTAs share every
   weight unit, one issuer feeds both SMs) computes the same per-row arithmetic, so
   its outputs equal the default tcgen05 kernel's bit for bit - including ragged
-  sizes where the follower CTA's tile lies beyond the end."""
+  sizes where the follower CTA's tile lies beyond the end.  The release library reads
+  no environment variables: this runs only against a developer build
+  (`python tools/build_variant.py dev -DNFB_DEV_KNOBS`, loaded through NFB_LIB_PATH)."""
+  from nerfies_b200 import _lib
+  if 'libnfb_dev' not in _lib.LIB_PATH:
+    pytest.skip('needs the -DNFB_DEV_KNOBS developer build (NFB_LIB_PATH=nerfies_b200/_variants/libnfb_dev.so)')
   spec = O.OracleSpec(num_coarse_samples=128, num_fine_samples=128, near=0.02, far=0.83,
                       num_nerf_point_freqs=8, sigma_activation='softplus', use_warp=True,
                       use_appearance_metadata=True, num_warp_embeddings=9,

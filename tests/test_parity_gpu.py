@@ -261,15 +261,19 @@ def test_use_warp_false_override():
 # ---------------------------------------------------------------------------
 # Oracle comparisons at larger sizes (gin-file dimensions).
 # ---------------------------------------------------------------------------
-def _oracle_case(spec, num_rays, seed, alpha):
+def _oracle_case(spec, num_rays, seed, alpha, precision='fp32'):
   p = O.make_trained_like(O.init_params(spec, seed), seed=seed + 1)
   rays = O.synthetic_rays(num_rays, spec, seed=seed + 2)
-  model = model_from_spec(spec_to_dict(spec), device=DEV, batch_size=num_rays)
+  model = model_from_spec(spec_to_dict(spec), device=DEV, batch_size=num_rays,
+                          precision=precision)
   return p, rays, model
 
 
+# Both parity-holding modes: fp32 (CUDA cores) and fp16x3 (tcgen05, three fp16 MMA
+# chains per layer into one fp32 accumulator) must meet the same 1e-4 per stage.
+@pytest.mark.parametrize('precision', ['fp32', 'fp16x3'])
 @pytest.mark.parametrize('dims', ['quarterhd', 'vrig', 'fullhd_small'])
-def test_levels_vs_oracle(dims):
+def test_levels_vs_oracle(dims, precision):
   if dims == 'quarterhd':
     spec = O.OracleSpec(num_coarse_samples=128, num_fine_samples=128,
                         near=0.02, far=0.83, num_nerf_point_freqs=8,
@@ -291,7 +295,7 @@ def test_levels_vs_oracle(dims):
                         use_appearance_metadata=True, num_warp_embeddings=50,
                         num_appearance_embeddings=50)
     n, alpha = 33, 8.0   # ragged: 33*256 rows is not a multiple of the tile
-  p, rays, model = _oracle_case(spec, n, 5, alpha)
+  p, rays, model = _oracle_case(spec, n, 5, alpha, precision)
   ref = O.render_forward(p, spec, rays, warp_alpha=alpha, return_points=True)
   pg = tree_to_device(p, DEV)
   # The truth is the fp64 shadow; the fp32 oracle's own distance from it is the
@@ -304,7 +308,7 @@ def test_levels_vs_oracle(dims):
     for k in ('rgb', 'depth', 'acc', 'weights', 'warped_points'):
       band = rel_err(ref[level][k], r64[k])
       err = rel_err(got[k], r64[k])
-      _REPORT.append((dims, level, k, err, band))
+      _REPORT.append((f'{dims}[{precision}]', level, k, err, band))
       assert err < TOL + 2 * band, (
           f'{dims} {level}/{k}: err vs fp64 {err:.3e}, fp32 band {band:.3e}')
     assert med_depth_ok(got['med_depth'], ref[level], z)

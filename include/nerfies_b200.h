@@ -39,6 +39,12 @@ enum nfb_activation {
   NFB_ACT_TANH = 4, NFB_ACT_SIGMOID = 5, NFB_ACT_SOFTPLUS = 6
 };
 enum nfb_warp_type { NFB_WARP_NONE = 0, NFB_WARP_TRANSLATION = 1, NFB_WARP_SE3 = 2 };
+/* warp_metadata_encoder_type (configs.py:103; warping.py:109-123, 250-260):
+ * GLO   = GloEncoder on metadata['warp'] ids;
+ * TIME  = modules.TimeEncoder (modules.py:297-322) on metadata['time'], annealed by
+ *         warp_extra['time_alpha'];
+ * BLEND = (1 - time_alpha) * glo(id) + time_alpha * TimeEncoder(float(id)) (warping.py:128-133). */
+enum nfb_warp_encoder { NFB_WARP_ENC_GLO = 0, NFB_WARP_ENC_TIME = 1, NFB_WARP_ENC_BLEND = 2 };
 /* Arithmetic of the MLP GEMMs.  Everything else is always fp32. */
 enum nfb_precision {
   NFB_PREC_FP32 = 0,     /* fp32 FFMA on CUDA cores: general (any width / activation / condition) */
@@ -75,6 +81,11 @@ typedef struct nfb_config {
   int use_white_background, use_linear_disparity, use_sample_at_infinity;
   float near_plane, far_plane;   /* NerfModel.near / .far                       */
   int precision;                 /* nfb_precision                               */
+  /* warp-field variants (warping.py:84-123, 233-260, 242-243, 339-352) */
+  int warp_metadata_encoder;     /* nfb_warp_encoder: glo | time | blend (TranslationField only) */
+  int time_encoder_num_freqs;    /* warp_kwargs['metadata_encoder_num_freqs'] (TimeEncoder posenc) */
+  int warp_use_pivot;            /* SE3Field(use_pivot=True): branches_p          */
+  int warp_use_translation;      /* SE3Field(use_translation=True): branches_t    */
 } nfb_config;
 
 /* Flags for the render entry points. */
@@ -122,6 +133,12 @@ int nfb_render_forward(nfb_handle* h, int num_rays, const float* origins,
                        float* out_coarse, float* out_fine, float* w_coarse,
                        float* w_fine, float* z_fine, void* stream);
 
+/* warp_extra['time_alpha'] (model_utils.py:31-33; modules.py:317-320) for the
+ * TIME / BLEND warp metadata encoders; persists on the handle until changed
+ * (default 0).  With NFB_WARP_ENC_TIME the `warp_id` argument of the render / warp
+ * entry points is reinterpreted as const float* metadata['time'] (B). */
+int nfb_set_time_alpha(nfb_handle* h, float time_alpha);
+
 /* Same call with HOST buffers: stages inputs through pinned memory, H2D,
  * renders, D2H, synchronises.  This is what render_image's model_fn does per
  * chunk in the reference (evaluation.py:85-93: shard -> model_fn -> unshard). */
@@ -159,8 +176,10 @@ int nfb_coarse_z_vals(nfb_handle* h, int num_rays, const float* t_rand,
 /* warp_field.apply on free points (nerfies/warping.py:355-389, 160-199; called
  * by training.py:122-131): points (P,3), warp_id (P) -> warped (P,3). */
 int nfb_warp_forward(nfb_handle* h, int num_points, const float* points,
-                     const unsigned* warp_id, float warp_alpha, float* warped,
-                     void* stream);
+                     const unsigned* warp_id, float warp_alpha, unsigned flags,
+                     float* warped, void* stream);
+/* flags: NFB_FLAG_METADATA_ENCODED = warp_field.apply(..., metadata_encoded=True)
+ * (warping.py:186-187, 378): warp_id is (P, num_warp_features) float embeddings. */
 
 /* Measurement aid (bench.py's roofline): when enabled, every launch of the field
  * kernel (the dominant kernel) is bracketed by cudaEvents on its launch stream.

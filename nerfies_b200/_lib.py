@@ -18,12 +18,13 @@ SYMBOLS = [
     'nfb_warp_forward', 'nfb_kernel_launches', 'nfb_last_error', 'nfb_version',
     'nfb_set_profiling', 'nfb_field_time_ms', 'nfb_selftest_gemm', 'nfb_set_trace', 'nfb_selftest_microbench',
     'nfb_camera_rays', 'nfb_pixels_to_rays', 'nfb_selftest_gemm2',
-    'nfb_debug_provoke_timeout',
+    'nfb_debug_provoke_timeout', 'nfb_set_time_alpha',
 ]
 
 ACTIVATIONS = {'none': 0, 'relu': 1, 'elu': 2, 'leaky_relu': 3, 'tanh': 4,
                'sigmoid': 5, 'softplus': 6}
 WARP_TYPES = {None: 0, 'none': 0, 'translation': 1, 'se3': 2}
+WARP_ENCODERS = {'glo': 0, 'time': 1, 'blend': 2}
 PRECISIONS = {'fp32': 0, 'bf16': 1, 'fp16x3': 2}
 FLAG_COARSE_ONLY = 1
 FLAG_NO_WARP = 2
@@ -69,6 +70,10 @@ class NfbConfig(ctypes.Structure):
       ('near_plane', ctypes.c_float),
       ('far_plane', ctypes.c_float),
       ('precision', ctypes.c_int),
+      ('warp_metadata_encoder', ctypes.c_int),
+      ('time_encoder_num_freqs', ctypes.c_int),
+      ('warp_use_pivot', ctypes.c_int),
+      ('warp_use_translation', ctypes.c_int),
   ]
 
 
@@ -132,7 +137,9 @@ def load():
   lib.nfb_sample_pdf.restype = ci
   lib.nfb_coarse_z_vals.argtypes = [vp, ci, vp, vp, vp]
   lib.nfb_coarse_z_vals.restype = ci
-  lib.nfb_warp_forward.argtypes = [vp, ci, vp, vp, cf, vp, vp]
+  lib.nfb_warp_forward.argtypes = [vp, ci, vp, vp, cf, cu, vp, vp]
+  lib.nfb_set_time_alpha.argtypes = [vp, cf]
+  lib.nfb_set_time_alpha.restype = ci
   lib.nfb_warp_forward.restype = ci
   lib.nfb_kernel_launches.argtypes = [vp]
   lib.nfb_kernel_launches.restype = ctypes.c_longlong

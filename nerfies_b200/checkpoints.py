@@ -57,7 +57,10 @@ def _unchunk(tree):
     if tree.get('__msgpack_chunked_array__'):
       chunks = tree['chunks']
       flat = np.concatenate([np.asarray(chunks[str(i)]).reshape(-1) for i in range(len(chunks))])
-      return flat.reshape(tuple(tree['shape']))
+      shape = tree['shape']
+      if isinstance(shape, dict):      # flax writes _tuple_to_dict(shape): {'0': d0, '1': d1, ...}
+        shape = [shape[str(i)] for i in range(len(shape))]
+      return flat.reshape(tuple(int(d) for d in shape))
     return {k: _unchunk(v) for k, v in tree.items()}
   return tree
 
@@ -94,7 +97,9 @@ def _chunk(tree):
     flat = tree.reshape(-1)
     per = max(1, _MAX_CHUNK_BYTES // tree.dtype.itemsize)
     chunks = {str(i): flat[s:s + per] for i, s in enumerate(range(0, flat.size, per))}
-    return {'__msgpack_chunked_array__': True, 'shape': tuple(tree.shape), 'chunks': chunks}
+    # flax (serialization._chunk): the shape travels as _tuple_to_dict(shape), like `chunks`
+    return {'__msgpack_chunked_array__': True,
+            'shape': {str(i): int(d) for i, d in enumerate(tree.shape)}, 'chunks': chunks}
   return tree
 
 

@@ -34,6 +34,7 @@ struct FieldProgram {
   Net warp;                // SE3Field / TranslationField trunk + heads
   Net nerf;                // NerfMLP trunk, bottleneck, alpha head, rgb branch
   int warp_type;           // 0 none, 1 translation, 2 se3
+  int warp_pivot, warp_trans;  // SE3Field use_pivot / use_translation: heads [w v (p) (t)]
   int Fw, G, Dw;           // warp inputs: [3 + 6 Fw posenc | G glo code]
   int Fp, Dp;              // nerf inputs: [3 + 6 Fp posenc | tc | ac | rc]
   int tc, ac, rc;
@@ -84,8 +85,13 @@ __device__ __forceinline__ float posenc_feature(const float x[3], int f) {
 // SE3Field.warp tail (warping.py:330-345) + rigid_body.exp_se3
 // (rigid_body.py:54-89), written exactly as the reference does (no small-angle
 // guard).  wv = [w(3), v(3)] raw head outputs, x the sample point.
-__device__ __forceinline__ void se3_apply(const float wv[6], const float x[3],
-                                          float out[3]) {
+// pivot / trans (nullable): SE3Field use_pivot / use_translation (warping.py:339-352):
+// x + pivot -> rigid transform -> - pivot -> + trans.
+__device__ __forceinline__ void se3_apply(const float wv[6], const float x_in[3],
+                                          float out[3], const float* pivot = nullptr,
+                                          const float* trans = nullptr) {
+  float x[3] = {x_in[0], x_in[1], x_in[2]};
+  if (pivot) { x[0] = x[0] + pivot[0]; x[1] = x[1] + pivot[1]; x[2] = x[2] + pivot[2]; }
   float theta = sqrtf(wv[0] * wv[0] + wv[1] * wv[1] + wv[2] * wv[2]);
   float w0 = wv[0] / theta, w1 = wv[1] / theta, w2 = wv[2] / theta;
   float v0 = wv[3] / theta, v1 = wv[4] / theta, v2 = wv[5] / theta;
@@ -113,6 +119,8 @@ __device__ __forceinline__ void se3_apply(const float wv[6], const float x[3],
     float rx = R[0] * x[0] + R[1] * x[1] + R[2] * x[2];
     out[i] = (rx + p) / 1.0f;
   }
+  if (pivot) { out[0] = out[0] - pivot[0]; out[1] = out[1] - pivot[1]; out[2] = out[2] - pivot[2]; }
+  if (trans) { out[0] = out[0] + trans[0]; out[1] = out[1] + trans[1]; out[2] = out[2] + trans[2]; }
 }
 
 }  // namespace nfb

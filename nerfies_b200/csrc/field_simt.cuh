@@ -219,10 +219,11 @@ field_simt_kernel(const __grid_constant__ FieldProgram prog, const FieldArgs arg
     if (part == 0) {
       float y[3];
       if (prog.warp_type == 2) {
-        float wv[6];
+        float wv[12];
 #pragma unroll
-        for (int q = 0; q < 6; ++q) wv[q] = sm.out[q * kRS + r];
-        se3_apply(wv, x, y);
+        for (int q = 0; q < 12; ++q) wv[q] = sm.out[q * kRS + r];
+        se3_apply(wv, x, y, prog.warp_pivot ? wv + 6 : nullptr,
+                  prog.warp_trans ? wv + (prog.warp_pivot ? 9 : 6) : nullptr);
       } else {
 #pragma unroll
         for (int c = 0; c < 3; ++c) y[c] = x[c] + sm.out[c * kRS + r];  // warping.py:156

@@ -742,14 +742,15 @@ field_tc_kernel(const __grid_constant__ TcProgram prog, const __grid_constant__ 
           tmem_ld16(t_lane, v);
           tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 8; j += 4) {
+          for (int j = 0; j < 12; j += 4) {
             const float4 bq = bias4[j >> 2];
             v[j] += bq.x; v[j + 1] += bq.y; v[j + 2] += bq.z; v[j + 3] += bq.w;
           }
           if (st.epi == kEpiWarpHeads) {
             float y[3];
             if (prog.warp_type == 2) {
-              se3_apply(v, row.x, y);
+              se3_apply(v, row.x, y, prog.warp_pivot ? v + 6 : nullptr,
+                        prog.warp_trans ? v + (prog.warp_pivot ? 9 : 6) : nullptr);
             } else {
 #pragma unroll
               for (int c = 0; c < 3; ++c) y[c] = row.x[c] + v[c];
@@ -813,6 +814,7 @@ inline int build_tc_program(nfb_handle* h, int level, long long* wbytes, long lo
   // has two weight units [W_hi | W_lo], and "sub-tile 1" of a unit is the lo image.
   const bool x3 = h->cfg.precision == NFB_PREC_FP16X3;
   const int wparts = x3 ? 2 : 1;
+  tp.warp_pivot = fp.warp_pivot; tp.warp_trans = fp.warp_trans;
   tp.warp_type = fp.warp_type; tp.Fw = fp.Fw; tp.G = fp.G; tp.Fp = fp.Fp; tp.rc = fp.rc;
   tp.cond_stride = fp.cond_stride; tp.sigma_act = fp.sigma_act;
   if (fp.tc || fp.ac) return tc_fail("trunk/alpha conditions");
@@ -847,7 +849,7 @@ inline int build_tc_program(nfb_handle* h, int level, long long* wbytes, long lo
         if (t.src[kb] < kSrcIn && t.src[kb] < t.chunk_n / kBlockK) t.kb_free = kb;
     } else {
       t.n_chunks = 1; t.chunk_n = 16; t.kb_free = -1;
-      if (st.n > 8) return tc_fail("head wider than 8");
+      if (st.n > 12) return tc_fail("head wider than 12");
     }
     t.b_off = new_bias(st);
     // weight units: for chunk c, for kb: chunk_n rows x 128 B

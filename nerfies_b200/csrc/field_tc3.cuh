@@ -489,7 +489,7 @@ field_x3_kernel(const __grid_constant__ TcProgram prog, const __grid_constant__ 
           tmem_ld16(t_lane, v);
           tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 8; j += 4) {
+          for (int j = 0; j < 12; j += 4) {
             const float4 bq = bias4[j >> 2];
             v[j] = fmaf(v[j], inv_s, bq.x); v[j + 1] = fmaf(v[j + 1], inv_s, bq.y);
             v[j + 2] = fmaf(v[j + 2], inv_s, bq.z); v[j + 3] = fmaf(v[j + 3], inv_s, bq.w);
@@ -497,7 +497,8 @@ field_x3_kernel(const __grid_constant__ TcProgram prog, const __grid_constant__ 
           if (st.epi == kEpiWarpHeads) {
             float y[3];
             if (prog.warp_type == 2) {
-              se3_apply(v, row.x, y);
+              se3_apply(v, row.x, y, prog.warp_pivot ? v + 6 : nullptr,
+                        prog.warp_trans ? v + (prog.warp_pivot ? 9 : 6) : nullptr);
             } else {
 #pragma unroll
               for (int c = 0; c < 3; ++c) y[c] = row.x[c] + v[c];

@@ -122,7 +122,27 @@ int build_programs(nfb_handle* h) {
   // Embedding tables come first in the parameter order (Flax names).
   Net warp{};
   if (use_warp) {
-    h->specs.push_back({"warp_field/metadata_encoder/embed/embedding", c.num_warp_embeddings, G, 0, G, 0, 1});
+    // metadata encoder of the warp field (warping.py:109-123, 250-260)
+    const int enc = c.warp_metadata_encoder;
+    if (enc < NFB_WARP_ENC_GLO || enc > NFB_WARP_ENC_BLEND) return fail("bad warp_metadata_encoder");
+    if (enc == NFB_WARP_ENC_BLEND && c.warp_field_type != NFB_WARP_TRANSLATION)
+      return fail("Unknown metadata encoder type 'blend' for the SE(3) field (warping.py:258-260)");
+    if (enc != NFB_WARP_ENC_TIME)
+      h->specs.push_back({std::string(enc == NFB_WARP_ENC_GLO ? "warp_field/metadata_encoder" : "warp_field/glo_encoder") +
+                          "/embed/embedding", c.num_warp_embeddings, G, 0, G, 0, 1});
+    if (enc != NFB_WARP_ENC_GLO) {
+      // modules.TimeEncoder (modules.py:297-322): depth 6, width 64, skips (4,), output = G features
+      const int F = c.time_encoder_num_freqs;
+      if (F < 0 || 1 + 2 * F > nfb::kTimeMaxIn) return fail("metadata_encoder_num_freqs=%d unsupported", F);
+      const std::string root = enc == NFB_WARP_ENC_TIME ? "warp_field/metadata_encoder/mlp" : "warp_field/time_encoder/mlp";
+      int tcur = nfb::kB0;
+      Net tn{};
+      if (build_mlp(b, tn, root, 6, 64, 1u << 4, 1 + 2 * F, 0, nfb::kRelu, nfb::kB0, 0, &tcur)) return -1;
+      tn.steps[tn.n_steps++] = b.dense({root + "/logit"}, 64, 0, 0, {G}, nfb::kNone, tcur, nfb::kOut0);
+      h->time_net = tn;
+    }
+    if (c.warp_field_type != NFB_WARP_SE3 && (c.warp_use_pivot || c.warp_use_translation))
+      return fail("use_pivot / use_translation are SE3Field arguments (warping.py:242-243)");
     int cur = nfb::kB0;
     const bool se3 = c.warp_field_type == NFB_WARP_SE3;
     const std::string mlp_name = se3 ? "warp_field/trunk" : "warp_field/mlp";
@@ -130,9 +150,12 @@ int build_programs(nfb_handle* h) {
     if (build_mlp(b, warp, mlp_name, c.warp_trunk_depth, c.warp_trunk_width, c.warp_skips_mask,
                   Dw, 0, nfb::kRelu, nfb::kB0, 0, &cur)) return -1;
     if (se3) {
-      warp.steps[warp.n_steps++] = b.dense(
-          {"warp_field/branches_w/logit", "warp_field/branches_v/logit"}, c.warp_trunk_width, 0, 0,
-          {3, 3}, nfb::kNone, cur, nfb::kOut0);
+      // heads side by side in N: [w v (p) (t)] (warping.py:269-303)
+      std::vector<std::string> names = {"warp_field/branches_w/logit", "warp_field/branches_v/logit"};
+      std::vector<int> ns = {3, 3};
+      if (c.warp_use_pivot) { names.push_back("warp_field/branches_p/logit"); ns.push_back(3); }
+      if (c.warp_use_translation) { names.push_back("warp_field/branches_t/logit"); ns.push_back(3); }
+      warp.steps[warp.n_steps++] = b.dense(names, c.warp_trunk_width, 0, 0, ns, nfb::kNone, cur, nfb::kOut0);
     } else {
       warp.steps[warp.n_steps++] = b.dense({"warp_field/mlp/logit"}, c.warp_trunk_width, 0, 0,
                                            {3}, nfb::kNone, cur, nfb::kOut0);
@@ -194,6 +217,7 @@ int build_programs(nfb_handle* h) {
     p.warp = warp;
     p.nerf = nerf;
     p.warp_type = c.warp_field_type;
+    p.warp_pivot = use_warp && c.warp_use_pivot; p.warp_trans = use_warp && c.warp_use_translation;
     p.Fw = c.num_warp_freqs; p.G = G; p.Dw = Dw;
     p.Fp = c.num_nerf_point_freqs; p.Dp = Dp;
     p.tc = tc; p.ac = ac; p.rc = rc;
@@ -298,8 +322,33 @@ int run_cond(nfb_handle* h, int B, const float* viewdirs, const unsigned* warp_i
   a.encoded = encoded;
   if (h->prog[0].G + h->prog[0].tc + h->prog[0].ac + h->prog[0].rc == 0) return 0;
   const long long total = (long long)B * a.stride;
+  const int enc = c.warp_field_type != NFB_WARP_NONE ? c.warp_metadata_encoder : NFB_WARP_ENC_GLO;
+  if (enc == NFB_WARP_ENC_TIME && !encoded) a.warp_id = nullptr;   // `warp_id` carries float timestamps
   nfb::ray_cond_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(a);
-  return launch_check(h, "ray_cond_kernel");
+  if (launch_check(h, "ray_cond_kernel")) return -1;
+  if (enc != NFB_WARP_ENC_GLO && !encoded && warp_id) {
+    // TimeEncoder on metadata['time'] ('time') or on float(id) ('blend', alpha = None)
+    nfb::TimeArgs t{};
+    t.params = h->d_packed; t.net = h->time_net;
+    t.F = c.time_encoder_num_freqs;
+    if (enc == NFB_WARP_ENC_TIME) t.time_f = reinterpret_cast<const float*>(warp_id);
+    else t.time_id = warp_id;
+    const float alpha = enc == NFB_WARP_ENC_TIME ? h->time_alpha : (float)t.F;   // modules.py:318-319
+    const float pi = 3.14159274101257324f;
+    for (int k = 0; k < t.F; ++k) {                     // cosine_easing_window (modules.py:274-294)
+      float x = alpha - (float)k;
+      x = fminf(fmaxf(x, 0.f), 1.f);
+      volatile float arg = pi * x;
+      arg = arg + pi;
+      volatile float cv = cosf(arg);
+      t.window[k] = 0.5f * (1.f + cv);
+    }
+    t.blend = enc == NFB_WARP_ENC_BLEND; t.time_alpha = h->time_alpha;
+    t.cond = h->d_cond; t.stride = h->cond_stride; t.G = h->prog[0].G; t.num_rays = B;
+    nfb::time_embed_kernel<<<(B + nfb::kTimeRays - 1) / nfb::kTimeRays, nfb::kTimeThreads, 0, s>>>(t);
+    return launch_check(h, "time_embed_kernel");
+  }
+  return 0;
 }
 
 int run_field(nfb_handle* h, int level, long long rows, int S, const float* origins,
@@ -402,6 +451,19 @@ int abort_check() {
   return 0;
 }
 
+// A handle's workspace (cond, z, samples, window table) is shared by its calls: work
+// of consecutive calls must be ordered.  Calls on ONE stream are; when the caller
+// switches streams the new stream first waits for the previous call's last kernel.
+int enter_stream(nfb_handle* h, cudaStream_t s) {
+  if (h->last_stream_valid && h->last_stream != s) {
+    if (!h->ev_order) NFB_CUDA(cudaEventCreateWithFlags(&h->ev_order, cudaEventDisableTiming));
+    NFB_CUDA(cudaEventRecord(h->ev_order, h->last_stream));
+    NFB_CUDA(cudaStreamWaitEvent(s, h->ev_order, 0));
+  }
+  h->last_stream = s; h->last_stream_valid = true;
+  return 0;
+}
+
 int check_call(nfb_handle* h, int B) {
   if (!h) return fail("null handle");
   if (abort_check()) return -1;
@@ -470,6 +532,12 @@ int nfb_set_trace(nfb_handle* h, long long* buffer, int capacity) {
 int nfb_debug_provoke_timeout(nfb_handle* h, int enabled) {
   if (!h) return fail("null handle");
   h->debug_bits = enabled ? 8 : 0;
+  return 0;
+}
+
+int nfb_set_time_alpha(nfb_handle* h, float time_alpha) {
+  if (!h) return fail("null handle");
+  h->time_alpha = time_alpha;
   return 0;
 }
 
@@ -644,6 +712,7 @@ void nfb_destroy(nfb_handle* h) {
   if (h->h_in) cudaFreeHost(h->h_in);
   if (h->h_out) cudaFreeHost(h->h_out);
   if (h->h_ids) cudaFreeHost(h->h_ids);
+  if (h->ev_order) cudaEventDestroy(h->ev_order);
   delete h;
 }
 
@@ -669,6 +738,7 @@ int nfb_set_params(nfb_handle* h, const float* const* tensors, const long long* 
   if (count != (int)h->specs.size())
     return fail("expected %d parameter tensors, got %d", (int)h->specs.size(), count);
   cudaStream_t s = (cudaStream_t)stream;
+  if (enter_stream(h, s)) return -1;
   for (int i = 0; i < count; ++i) {
     const ParamSpec& p = h->specs[i];
     if (numels[i] != p.rows * p.cols)
@@ -693,6 +763,7 @@ int nfb_set_params(nfb_handle* h, const float* const* tensors, const long long* 
 int nfb_coarse_z_vals(nfb_handle* h, int B, const float* t_rand, float* z, void* stream) {
   if (check_call(h, B)) return -1;
   if (B == 0) return 0;
+  if (enter_stream(h, (cudaStream_t)stream)) return -1;
   const int nc = h->cfg.num_coarse_samples;
   const long long total = (long long)B * nc;
   nfb::coarse_z_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
@@ -705,6 +776,7 @@ int nfb_sample_pdf(nfb_handle* h, int B, const float* z_coarse, const float* w_c
   if (check_call(h, B)) return -1;
   if (h->cfg.num_fine_samples <= 0) return fail("model has no fine level");
   if (B == 0) return 0;
+  if (enter_stream(h, (cudaStream_t)stream)) return -1;
   return run_resample(h, B, z_coarse, w_coarse, u_rand, z_fine, (cudaStream_t)stream);
 }
 
@@ -719,6 +791,7 @@ int nfb_render_samples(nfb_handle* h, int level, int B, int S, const float* z_va
   if (S < 1 || (!samples && S > smax)) return fail("num_samples=%d exceeds the workspace (%d)", S, smax);
   if (B == 0) return 0;
   cudaStream_t s = (cudaStream_t)stream;
+  if (enter_stream(h, s)) return -1;
   if (set_window(h, warp_alpha, s)) return -1;
   if (run_cond(h, B, viewdirs ? viewdirs : directions, warp_id, app_id, cam_id, s,
                (flags & NFB_FLAG_METADATA_ENCODED) != 0)) return -1;
@@ -739,6 +812,7 @@ int nfb_render_forward(nfb_handle* h, int B, const float* origins, const float* 
   if (B == 0) return 0;
   const nfb_config& c = h->cfg;
   cudaStream_t s = (cudaStream_t)stream;
+  if (enter_stream(h, s)) return -1;
   const int nc = c.num_coarse_samples, nfine = nc + c.num_fine_samples;
   const bool use_warp = !(flags & NFB_FLAG_NO_WARP);
   const bool fine = c.num_fine_samples > 0 && !(flags & NFB_FLAG_COARSE_ONLY);
@@ -771,12 +845,12 @@ int nfb_render_forward_host(nfb_handle* h, int B, const float* origins, const fl
     return fail("NFB_FLAG_METADATA_ENCODED is only supported by the device entry points");
   if (B == 0) return 0;
   cudaStream_t s = (cudaStream_t)stream;
+  if (enter_stream(h, s)) return -1;
   const size_t mr = h->max_rays;
-  if (!h->h_in) {
-    NFB_CUDA(cudaMallocHost(&h->h_in, mr * 9 * sizeof(float)));
-    NFB_CUDA(cudaMallocHost(&h->h_out, mr * 12 * sizeof(float)));
-    NFB_CUDA(cudaMallocHost(&h->h_ids, mr * 3 * sizeof(unsigned)));
-  }
+  // (each buffer on its own: a failed allocation leaves the others usable for the retry)
+  if (!h->h_in) NFB_CUDA(cudaMallocHost(&h->h_in, mr * 9 * sizeof(float)));
+  if (!h->h_out) NFB_CUDA(cudaMallocHost(&h->h_out, mr * 12 * sizeof(float)));
+  if (!h->h_ids) NFB_CUDA(cudaMallocHost(&h->h_ids, mr * 3 * sizeof(unsigned)));
   const size_t n3 = (size_t)B * 3;
   memcpy(h->h_in, origins, n3 * sizeof(float));
   memcpy(h->h_in + mr * 3, directions, n3 * sizeof(float));
@@ -810,15 +884,16 @@ int nfb_render_forward_host(nfb_handle* h, int B, const float* origins, const fl
 }
 
 int nfb_warp_forward(nfb_handle* h, int P, const float* points, const unsigned* warp_id,
-                     float warp_alpha, float* warped, void* stream) {
+                     float warp_alpha, unsigned flags, float* warped, void* stream) {
   if (check_call(h, P)) return -1;
   if (h->cfg.warp_field_type == NFB_WARP_NONE) return fail("model has no warp field");
   if (P == 0) return 0;
   cudaStream_t s = (cudaStream_t)stream;
+  if (enter_stream(h, s)) return -1;
   if (set_window(h, warp_alpha, s)) return -1;
   // Only the GLO block of the condition vector is read in warp-only mode; the
   // view-direction block is computed from `points` and ignored.
-  if (run_cond(h, P, points, warp_id, nullptr, nullptr, s)) return -1;
+  if (run_cond(h, P, points, warp_id, nullptr, nullptr, s, (flags & NFB_FLAG_METADATA_ENCODED) != 0)) return -1;
   // Free points: rows = points, z = 0 (x = p + 0 * p = p exactly for finite p).
   return run_field(h, 0, P, 1, points, points, nullptr, nullptr, warped, true, true, s);
 }

@@ -86,6 +86,11 @@ struct nfb_handle {
   bool ev_valid[2] = {false, false};
   int cond_stride = 0;
   int sm_count = 148;
+  nfb::Net time_net{};                // TimeEncoder MLP ('time' / 'blend' warp metadata encoders)
+  float time_alpha = 0.f;             // warp_extra['time_alpha'] (nfb_set_time_alpha)
+  cudaStream_t last_stream = nullptr;  // stream of the previous call (see enter_stream)
+  bool last_stream_valid = false;
+  cudaEvent_t ev_order = nullptr;
   int debug_bits = 0;                 // FieldArgs::debug bits set through the test hook (abort-path test)
   long long* trace = nullptr;
   int trace_cap = 0;

@@ -84,6 +84,93 @@ __global__ void ray_cond_kernel(const CondArgs a) {
 }
 
 // ---------------------------------------------------------------------------
+// modules.TimeEncoder (modules.py:297-322) per ray: annealed positional encoding
+// of the timestamp, MLP(depth 6, width 64, skips (4,)) + `features`-wide output
+// layer; writes (or, 'blend' encoder of TranslationField, warping.py:128-133,
+// blends into) the warp-embedding block cond[:, 0:G].  fp32 FFMA, one CTA per
+// kTimeRays rays, thread j owns output channel j.  Per-ray work (~26 K MAC) is
+// negligible next to the per-sample field evaluation.
+// ---------------------------------------------------------------------------
+constexpr int kTimeRays = 8;
+constexpr int kTimeThreads = 128;
+constexpr int kTimeMaxIn = 40;     // 1 + 2 F, F <= 19
+
+struct TimeArgs {
+  const float* params;           // packed dense buffer
+  Net net;                       // hidden layers + output layer
+  const float* time_f;           // (B) float timestamps, or null
+  const unsigned* time_id;       // (B) ids used as timestamps ('blend': float(id)), or null
+  int F;                         // metadata_encoder_num_freqs
+  float window[20];              // cosine_easing_window(F, time_alpha)
+  int blend;
+  float time_alpha;
+  float* cond;                   // (B, stride): block [0, G) is read (blend) / written
+  int stride, G, num_rays;
+};
+
+__global__ void __launch_bounds__(kTimeThreads)
+time_embed_kernel(const __grid_constant__ TimeArgs a) {
+  __shared__ float xbuf[2][kTimeRays][kMaxWidth];
+  __shared__ float in[kTimeRays][kTimeMaxIn];
+  const int tid = threadIdx.x;
+  const int ray0 = blockIdx.x * kTimeRays;
+  const int din = 1 + 2 * a.F;
+  for (int i = tid; i < kTimeRays * din; i += kTimeThreads) {
+    const int r = i / din, k = i - r * din;
+    const int ray = min(ray0 + r, a.num_rays - 1);
+    const float t = a.time_f ? a.time_f[ray] : (float)a.time_id[ray];
+    float v;
+    if (k == 0) {
+      v = t;
+    } else {
+      // features [sin(2^f t)]_f, then... per frequency: sin, sin(. + pi/2) (modules.py:213-228 with C = 1)
+      const int f = (k - 1) >> 1, which = (k - 1) & 1;
+      float ang = t * exp2f((float)f);
+      if (which) ang = ang + kHalfPiF;
+      v = a.window[f] * sinf(ang);
+    }
+    in[r][k] = v;
+  }
+  __syncthreads();
+  int cur = 0;
+  for (int s = 0; s < a.net.n_steps; ++s) {
+    const Step& st = a.net.steps[s];
+    const float* W = a.params + st.w_off;
+    const float* src = xbuf[cur][0];
+    float* dst = xbuf[cur ^ 1][0];
+    for (int j = tid; j < st.n; j += kTimeThreads) {
+      float acc[kTimeRays];
+#pragma unroll
+      for (int r = 0; r < kTimeRays; ++r) acc[r] = 0.f;
+      for (int k = 0; k < st.k_x; ++k) {
+        const float w = __ldg(W + (size_t)k * st.npad + j);
+#pragma unroll
+        for (int r = 0; r < kTimeRays; ++r) acc[r] = fmaf(src[r * kMaxWidth + k], w, acc[r]);
+      }
+      for (int k = 0; k < st.k_in; ++k) {
+        const float w = __ldg(W + (size_t)(st.k_x + k) * st.npad + j);
+#pragma unroll
+        for (int r = 0; r < kTimeRays; ++r) acc[r] = fmaf(in[r][st.in_off + k], w, acc[r]);
+      }
+      const float b = __ldg(a.params + st.b_off + j);
+#pragma unroll
+      for (int r = 0; r < kTimeRays; ++r) dst[r * kMaxWidth + j] = apply_act(acc[r] + b, st.act);
+    }
+    __syncthreads();
+    cur ^= 1;
+  }
+  for (int i = tid; i < kTimeRays * a.G; i += kTimeThreads) {
+    const int r = i / a.G, q = i - r * a.G;
+    const int ray = ray0 + r;
+    if (ray >= a.num_rays) continue;
+    float v = xbuf[cur][r][q];
+    float* c = a.cond + (size_t)ray * a.stride + q;
+    if (a.blend) v = (1.0f - a.time_alpha) * *c + a.time_alpha * v;     // warping.py:132-133
+    *c = v;
+  }
+}
+
+// ---------------------------------------------------------------------------
 // sample_along_rays z_vals (model_utils.py:56-70).  z_lin/lower/upper are the
 // per-model tables built on the host exactly as the reference builds them.
 // ---------------------------------------------------------------------------

@@ -57,6 +57,7 @@ struct TcProgram {
   int unit_begin[kMaxTcSteps + 1];    // first unit of every step
   TcUnit units[kMaxTcUnits];
   int warp_type, Fw, G, Fp, rc, cond_stride, sigma_act;
+  int warp_pivot, warp_trans;     // SE3Field use_pivot / use_translation
   int alpha_w_off, alpha_b_off;   // aux float offsets
   int scale_off;                  // fp16x3: aux offset of the per-step max |W| (kMaxTcSteps floats)
   uint32_t units_per_pair;        // weight units streamed per tile pair

@@ -89,14 +89,26 @@ class _Handle:
     except Exception:  # pylint: disable=broad-except
       pass
 
-  def set_params(self, params: Mapping[str, Any]):
+  def set_params(self, params: Mapping[str, Any], partial: bool = False):
+    """Uploads the parameter pytree.  partial=True (warp_field.apply with the warp
+    subtree only): parameters missing from `params` keep the tensors of the last
+    upload, or zeros when there was none."""
     tensors = []
-    for name, rows, cols in self.param_specs:
+    last = getattr(self, '_keepalive', None)
+    for idx, (name, rows, cols) in enumerate(self.param_specs):
       node = params
+      missing = False
       for part in name.split('/'):
-        if part not in node:
-          raise KeyError(f'parameter {name!r} missing from the params pytree')
+        if not isinstance(node, Mapping) or part not in node:
+          missing = True
+          break
         node = node[part]
+      if missing:
+        if not partial or name.startswith('warp_field/'):
+          raise KeyError(f'parameter {name!r} missing from the params pytree')
+        tensors.append(last[idx] if last is not None else
+                       torch.zeros(rows * cols, device=self.device))
+        continue
       t = node
       if not torch.is_tensor(t):
         t = torch.as_tensor(t)
@@ -184,20 +196,27 @@ class NerfModel:
     self._handle = None
 
     if noise_std is not None and noise_std > 0.0 and use_stratified_sampling:
-      raise NotImplementedError('noise_regularize (model_utils.py:266-282) is '
-                                'not implemented; no shipped config sets it')
+      # The reference itself cannot run this branch: NerfModel.render_samples hands the
+      # NerfMLP's output DICT to noise_regularize, which indexes it as an array
+      # (models.py:272-275 vs model_utils.py:278-280) -> TypeError.  Same error type here.
+      raise TypeError("noise_std > 0 with stratified sampling: the reference's "
+                      "noise_regularize (model_utils.py:266-282) raises on the NerfMLP's dict "
+                      'output (models.py:274); there is no behaviour to reproduce')
     if self.use_warp:
-      if warp_metadata_encoder_type != 'glo':
-        raise NotImplementedError(
-            "warp_metadata_encoder_type='time' (modules.TimeEncoder) is not "
-            'implemented; every shipped config uses glo')
       if warp_field_type not in ('se3', 'translation'):
         raise ValueError(f'Unknown warp field type: {warp_field_type!r}')
-      allowed = ({'trunk_depth', 'trunk_width', 'skips'} if warp_field_type ==
-                 'se3' else {'depth', 'hidden_channels', 'skips'})
+      ok_enc = ('glo', 'time') if warp_field_type == 'se3' else ('glo', 'time', 'blend')
+      if warp_metadata_encoder_type not in ok_enc:
+        # warping.py:121-123 / 258-260
+        raise ValueError(f'Unknown metadata encoder type {warp_metadata_encoder_type}')
+      allowed = ({'trunk_depth', 'trunk_width', 'skips', 'use_pivot', 'use_translation',
+                  'metadata_encoder_num_freqs'} if warp_field_type == 'se3' else
+                 {'depth', 'hidden_channels', 'skips', 'metadata_encoder_num_freqs'})
       extra = set(self.warp_kwargs) - allowed
       if extra:
-        raise NotImplementedError(f'warp_kwargs {sorted(extra)} not supported')
+        raise NotImplementedError(
+            f'warp_kwargs {sorted(extra)} not supported (rotation/pivot/translation branch '
+            'depths > 0, min/max_freq_log2, use_identity_map=False, custom initialisers)')
     if precision not in _lib.PRECISIONS:
       raise ValueError(f'precision must be one of {list(_lib.PRECISIONS)}')
 
@@ -227,6 +246,18 @@ class NerfModel:
   @property
   def warp_skips(self):
     return tuple(self.warp_kwargs.get('skips', (4,)))
+
+  @property
+  def metadata_encoder_num_freqs(self):
+    return int(self.warp_kwargs.get('metadata_encoder_num_freqs', 1))
+
+  @property
+  def warp_use_pivot(self):
+    return bool(self.warp_kwargs.get('use_pivot', False))
+
+  @property
+  def warp_use_translation(self):
+    return bool(self.warp_kwargs.get('use_translation', False))
 
   # -- C ABI plumbing ---------------------------------------------------------
   def nfb_config(self) -> _lib.NfbConfig:
@@ -268,6 +299,10 @@ class NerfModel:
     c.near_plane = self.near
     c.far_plane = self.far
     c.precision = _lib.PRECISIONS[self.precision]
+    c.warp_metadata_encoder = _lib.WARP_ENCODERS[self.warp_metadata_encoder_type]
+    c.time_encoder_num_freqs = self.metadata_encoder_num_freqs
+    c.warp_use_pivot = int(self.warp_use_pivot)
+    c.warp_use_translation = int(self.warp_use_translation)
     return c
 
   def handle(self, num_rays: int = 0) -> _Handle:
@@ -338,6 +373,7 @@ class NerfModel:
     params = variables['params']
     warp_extra = warp_extra or {'alpha': 0.0, 'time_alpha': 0.0}
     alpha = float(warp_extra.get('alpha', 0.0))
+    time_alpha = warp_extra.get('time_alpha')
     dev = self.device
     origins = _prep_f32(rays_dict['origins'], dev)
     directions = _prep_f32(rays_dict['directions'], dev)
@@ -366,13 +402,19 @@ class NerfModel:
       app_id = enc('appearance', self.num_appearance_features, self.use_appearance_metadata)
       cam_id = enc('camera', self.num_camera_features, self.use_camera_metadata)
     else:
-      warp_id = _prep_ids(md.get('warp'), dev) if self.use_warp else None
+      if self.use_warp and self.warp_metadata_encoder_type == 'time':
+        # models.py:252-254: the warp field reads metadata['time'] (B,1) float32
+        t = md.get('time')
+        warp_id = None if t is None else _prep_f32(t, dev).reshape(-1)
+      else:
+        warp_id = _prep_ids(md.get('warp'), dev) if self.use_warp else None
       app_id = (_prep_ids(md.get('appearance'), dev)
                 if self.use_appearance_metadata else None)
       cam_id = (_prep_ids(md.get('camera'), dev)
                 if self.use_camera_metadata else None)
     if self.use_warp and use_warp and warp_id is None:
-      raise KeyError("rays_dict['metadata']['warp'] is required")
+      key = 'time' if self.warp_metadata_encoder_type == 'time' else 'warp'
+      raise KeyError(f"rays_dict['metadata']['{key}'] is required")
     return_weights = self.use_weights or return_weights
     if t_rand is None and u_rand is None:
       t_rand, u_rand = self._draws(rngs, B)
@@ -384,6 +426,7 @@ class NerfModel:
     hd = self.handle(B)
     hd.set_params(params)
     lib, h = hd.lib, hd.h
+    self._set_time_alpha(hd, time_alpha)
     nc, nf = self.num_coarse_samples, self.num_fine_samples
     flags = 0 if use_warp else _lib.FLAG_NO_WARP
     if metadata_encoded:
@@ -438,12 +481,27 @@ class NerfModel:
         ret['z_vals'] = z
       return ret
 
+    if _packed:
+      # evaluation.py: the (B,6) buffers the C ABI wrote (rgb3, depth, med_depth, acc) -
+      # one contiguous block per level, so a frame's collective moves them unsplit
+      return {'coarse': out_c, 'fine': out_f} if nf > 0 else {'coarse': out_c}
     out['coarse'] = pack(out_c, w_c, 'coarse')
     if nf > 0:
       out['fine'] = pack(out_f, w_f, 'fine')
     return out
 
   __call__ = apply
+
+  def _set_time_alpha(self, hd, time_alpha):
+    """warp_extra['time_alpha'] for the 'time' / 'blend' encoders (None -> the
+    TimeEncoder's num_freqs, modules.py:318-319; 'blend' needs a number)."""
+    if not self.use_warp or self.warp_metadata_encoder_type == 'glo':
+      return
+    if time_alpha is None:
+      if self.warp_metadata_encoder_type == 'blend':
+        raise TypeError("warp_extra['time_alpha'] is required by the 'blend' encoder (warping.py:132)")
+      time_alpha = float(self.metadata_encoder_num_freqs)
+    _lib.check(hd.lib.nfb_set_time_alpha(hd.h, float(time_alpha)))
 
   def apply_host(self, variables, rays_dict, warp_extra=None):
     """End-to-end call on HOST (numpy / CPU torch) buffers: pinned staging,
@@ -491,30 +549,38 @@ class WarpField:
 
   def apply(self, variables, points, metadata, extra, return_jacobian=False,
             metadata_encoded=False):
+    """`variables` = {'params': params['warp_field']} as the reference call site passes
+    it (training.py:127-131) - or the whole model tree.  The given warp parameters
+    are uploaded on every call whose tensors changed; with the subtree only, the
+    non-warp parameters keep their last uploaded values (zeros if none were ever
+    uploaded - the warp-only launch does not read them)."""
     if return_jacobian:
       raise NotImplementedError('warp Jacobian: training tier (SURVEY §8f #2)')
-    if metadata_encoded:
-      raise NotImplementedError('metadata_encoded=True is not implemented')
     m = self.model
     dev = m.device
     pts = _prep_f32(points, dev)
     shape = pts.shape
     pts = pts.reshape(-1, 3)
-    ids = _prep_ids(torch.as_tensor(metadata).reshape(pts.shape[0], -1), dev)
-    hd = m.handle(pts.shape[0])
-    # accept either {'params': warp_field_params} or the whole model tree.
-    p = variables['params']
-    if 'warp_field' not in p:
-      if hd.param_key is None:
-        raise ValueError('pass the full model params once (model.apply) before '
-                         'calling warp_field.apply with the warp subtree only')
+    P = pts.shape[0]
+    if metadata_encoded:                                   # warping.py:186-187, 378
+      ids = _prep_f32(metadata, dev).reshape(P, -1)
+      if ids.shape[1] != m.num_warp_features:
+        raise ValueError(f'metadata_encoded=True: metadata must be (P, {m.num_warp_features})')
+      ids = ids.contiguous()
+      flags = _lib.FLAG_METADATA_ENCODED
+    elif m.warp_metadata_encoder_type == 'time':
+      ids, flags = _prep_f32(metadata, dev).reshape(-1), 0
     else:
-      hd.set_params(p)
+      ids, flags = _prep_ids(torch.as_tensor(metadata).reshape(P, -1), dev), 0
+    hd = m.handle(P)
+    p = variables['params']
+    hd.set_params(p if 'warp_field' in p else {'warp_field': p}, partial=True)
+    m._set_time_alpha(hd, extra.get('time_alpha'))
     out = torch.empty_like(pts)
     with torch.cuda.device(dev):
       _lib.check(hd.lib.nfb_warp_forward(
-          hd.h, pts.shape[0], _ptr(pts), _ptr(ids),
-          float(extra.get('alpha', 0.0)), _ptr(out), _stream()))
+          hd.h, P, _ptr(pts), _ptr(ids), float(extra.get('alpha', 0.0)), flags,
+          _ptr(out), _stream()))
     return {'warped_points': out.reshape(shape)}
 
 
@@ -566,13 +632,26 @@ def init_params(model: NerfModel, key) -> Dict[str, Any]:
   params = {}
   if model.use_warp:
     dw = 3 + 6 * model.num_warp_freqs + model.num_warp_features
-    wf = {'metadata_encoder': embed(model.num_warp_embeddings,
-                                    model.num_warp_features)}
+    glo = lambda: embed(model.num_warp_embeddings, model.num_warp_features)
+    # modules.TimeEncoder (modules.py:297-315): xavier hidden layers, U[0,0.05) output layer
+    tenc = lambda: {'mlp': mlp(1 + 2 * model.metadata_encoder_num_freqs, 6, 64, (4,),
+                               model.num_warp_features, 0.05)}
+    enc = model.warp_metadata_encoder_type
+    if enc == 'glo':
+      wf = {'metadata_encoder': glo()}
+    elif enc == 'time':
+      wf = {'metadata_encoder': tenc()}
+    else:
+      wf = {'glo_encoder': glo(), 'time_encoder': tenc()}
     if model.warp_field_type == 'se3':
       wf['trunk'] = mlp(dw, model.warp_trunk_depth, model.warp_trunk_width,
                         model.warp_skips)
       wf['branches_w'] = {'logit': dense(model.warp_trunk_width, 3, 1e-4)}
       wf['branches_v'] = {'logit': dense(model.warp_trunk_width, 3, 1e-4)}
+      if model.warp_use_pivot:
+        wf['branches_p'] = {'logit': dense(model.warp_trunk_width, 3, 1e-4)}
+      if model.warp_use_translation:
+        wf['branches_t'] = {'logit': dense(model.warp_trunk_width, 3, 1e-4)}
     else:
       wf['mlp'] = mlp(dw, model.warp_trunk_depth, model.warp_trunk_width,
                       model.warp_skips, 3, 1e-4)

@@ -101,7 +101,8 @@ ONLY = set(sys.argv[1:])   # optional: names of the cases to (re)generate
 
 def make_case(name, cfg_kwargs, *, num_rays, n_app, n_cam, n_warp, near, far,
               warp_alpha, seed, trained_like=True, stratified=False,
-              oracle_param_seed=None, store_params=True, encoded=False):
+              oracle_param_seed=None, store_params=True, encoded=False,
+              time_alpha=0.0):
   if ONLY and name not in ONLY:
     return
   cfg_kwargs = dict(cfg_kwargs)
@@ -144,7 +145,11 @@ def make_case(name, cfg_kwargs, *, num_rays, n_app, n_cam, n_warp, near, far,
       warp_field_type=cfg.warp_field_type,
       warp_trunk_depth=wk.get('trunk_depth', wk.get('depth', 6)),
       warp_trunk_width=wk.get('trunk_width', wk.get('hidden_channels', 128)),
-      warp_skips=list(wk.get('skips', (4,))))
+      warp_skips=list(wk.get('skips', (4,))),
+      warp_metadata_encoder_type=cfg.warp_metadata_encoder_type,
+      metadata_encoder_num_freqs=wk.get('metadata_encoder_num_freqs', 1),
+      warp_use_pivot=bool(wk.get('use_pivot', False)),
+      warp_use_translation=bool(wk.get('use_translation', False)))
   ospec = O.OracleSpec(**{**spec, 'nerf_skips': tuple(spec['nerf_skips']),
                           'warp_skips': tuple(spec['warp_skips'])})
 
@@ -169,7 +174,11 @@ def make_case(name, cfg_kwargs, *, num_rays, n_app, n_cam, n_warp, near, far,
       'metadata': {k: v.numpy().astype(np.uint32)
                    for k, v in rays_t['metadata'].items()},
   }
-  warp_extra = {'alpha': warp_alpha, 'time_alpha': 0.0}
+  if cfg.use_warp and cfg.warp_metadata_encoder_type == 'time':
+    # models.py:252-254: the warp field reads metadata['time'] (B,1) float32
+    rays['metadata']['time'] = np.random.default_rng(seed + 5).random(
+        (num_rays, 1)).astype(np.float32)
+  warp_extra = {'alpha': warp_alpha, 'time_alpha': time_alpha}
   del _DRAWS[:]
   del _ZFINE[:]
   out = model.apply({'params': params}, rays, warp_extra=warp_extra,
@@ -179,7 +188,7 @@ def make_case(name, cfg_kwargs, *, num_rays, n_app, n_cam, n_warp, near, far,
   draws = list(_DRAWS)
 
   blob = {'spec_json': np.array(json.dumps(spec)),
-          'warp_alpha': np.float32(warp_alpha),
+          'warp_alpha': np.float32(warp_alpha), 'time_alpha': np.float32(time_alpha),
           'rays/origins': rays['origins'], 'rays/directions': rays['directions']}
   for k, v in rays['metadata'].items():
     blob[f'rays/metadata/{k}'] = v
@@ -213,11 +222,18 @@ def make_case(name, cfg_kwargs, *, num_rays, n_app, n_cam, n_warp, near, far,
     rng = np.random.default_rng(seed + 3)
     pts = (rng.random((32, 3)) * 2 - 1).astype(np.float32)
     ids = rng.integers(0, n_warp, size=(32, 1)).astype(np.uint32)
+    if cfg.warp_metadata_encoder_type == 'time':
+      ids = rng.random((32, 1)).astype(np.float32)       # timestamps
     wout = wf.apply({'params': params['warp_field']}, pts, ids, warp_extra,
                     False, False)
     blob['warp/points'] = pts
     blob['warp/ids'] = ids
     blob['warp/warped_points'] = np.asarray(wout['warped_points'], np.float32)
+    # warp_field.apply(..., metadata_encoded=True) (warping.py:186-187, 378)
+    emb = (rng.standard_normal((32, cfg.num_warp_features)) * 0.05).astype(np.float32)
+    eout = wf.apply({'params': params['warp_field']}, pts, emb, warp_extra, False, True)
+    blob['warp/enc_embed'] = emb
+    blob['warp/enc_warped_points'] = np.asarray(eout['warped_points'], np.float32)
 
   # metadata_encoded=True (models.py:198-213,251; warping.py:186-187): the metadata
   # leaves are per-ray embeddings, deliberately NOT rows of the GLO tables.
@@ -313,6 +329,32 @@ def main():
       sigma_activation='softplus', warp_kwargs={'trunk_width': 32}),
             num_rays=10, n_app=4, n_cam=3, n_warp=5, near=0.02, far=0.83,
             warp_alpha=5.0, seed=18, encoded=True)
+
+
+  # I: warp_metadata_encoder_type='time' (modules.TimeEncoder on metadata['time'],
+  #    annealed by warp_extra['time_alpha']), SE(3) field.
+  make_case('time_small', dict(
+      small, use_warp=True, warp_field_type='se3', num_nerf_point_freqs=8,
+      num_warp_freqs=6, warp_metadata_encoder_type='time',
+      use_appearance_metadata=True, sigma_activation='softplus',
+      warp_kwargs={'trunk_width': 32, 'metadata_encoder_num_freqs': 3}),
+            num_rays=9, n_app=4, n_cam=1, n_warp=5, near=0.02, far=0.83,
+            warp_alpha=4.25, seed=19, time_alpha=1.6)
+  # J: TranslationField with the 'blend' encoder ((1-ta) glo + ta time, warping.py:128-133).
+  make_case('blend_small', dict(
+      small, use_warp=True, warp_field_type='translation', num_nerf_point_freqs=6,
+      num_warp_freqs=6, num_warp_features=4, warp_metadata_encoder_type='blend',
+      use_appearance_metadata=True, sigma_activation='softplus',
+      warp_kwargs={'hidden_channels': 32}),
+            num_rays=8, n_app=3, n_cam=1, n_warp=4, near=0.05, far=1.2,
+            warp_alpha=6.0, seed=20, time_alpha=0.35)
+  # K: SE3Field(use_pivot=True, use_translation=True) (warping.py:339-352).
+  make_case('pivot_small', dict(
+      small, use_warp=True, warp_field_type='se3', num_nerf_point_freqs=8,
+      num_warp_freqs=8, use_appearance_metadata=True, sigma_activation='softplus',
+      warp_kwargs={'trunk_width': 32, 'use_pivot': True, 'use_translation': True}),
+            num_rays=8, n_app=4, n_cam=1, n_warp=6, near=0.02, far=0.83,
+            warp_alpha=8.0, seed=21)
 
 
 if __name__ == '__main__':

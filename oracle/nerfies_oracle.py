@@ -80,6 +80,14 @@ class OracleSpec:
   warp_trunk_depth: int = 6
   warp_trunk_width: int = 128
   warp_skips: Tuple[int, ...] = (4,)
+  # metadata encoder of the warp field (warping.py:109-123, 250-260): 'glo',
+  # 'time' (modules.TimeEncoder on metadata['time']) or, TranslationField only,
+  # 'blend'; warp_kwargs['metadata_encoder_num_freqs'] (warping.py:84, 233).
+  warp_metadata_encoder_type: str = 'glo'
+  metadata_encoder_num_freqs: int = 1
+  # SE3Field(use_pivot=..., use_translation=...) (warping.py:242-243).
+  warp_use_pivot: bool = False
+  warp_use_translation: bool = False
 
 
 _ACTIVATIONS = {
@@ -256,6 +264,23 @@ def exp_se3(S: Tensor, theta: Tensor) -> Tuple[Tensor, Tensor]:
 # --------------------------------------------------------------------------
 # R3-R5  SE3Field  (warping.py:202-389)
 # --------------------------------------------------------------------------
+# TimeEncoder defaults (modules.py:301-304): not configurable through the model.
+TIME_ENCODER_DEPTH, TIME_ENCODER_WIDTH, TIME_ENCODER_SKIPS = 6, 64, (4,)
+
+
+def time_encode(params: Dict[str, Any], num_freqs: int, time: Tensor,
+                alpha: Optional[float], dtype) -> Tensor:
+  """modules.TimeEncoder.__call__ (modules.py:317-322): annealed positional
+  encoding of the (..., 1) timestamp, then MLP(depth 6, width 64, skips (4,))
+  with a `features`-wide output layer.  alpha None -> num_freqs."""
+  if alpha is None:
+    alpha = num_freqs
+  window = torch.from_numpy(cosine_easing_window(num_freqs, alpha))
+  enc = sinusoidal_encode(time.to(dtype), num_freqs, window)
+  return mlp(params['mlp'], enc, TIME_ENCODER_DEPTH, TIME_ENCODER_SKIPS, 'relu',
+             has_logit=True)
+
+
 def se3_field_warp(params: Dict[str, Any], spec: OracleSpec, points: Tensor,
                    metadata_embed: Tensor, alpha: float) -> Tensor:
   """SE3Field.warp (warping.py:322-353) for (..., 3) points with a matching
@@ -273,8 +298,17 @@ def se3_field_warp(params: Dict[str, Any], spec: OracleSpec, points: Tensor,
   R, p = exp_se3(torch.cat([w, v], dim=-1), theta)
   # from_homogenous(transform @ to_homogenous(x)) (rigid_body.py:92-97); the
   # homogeneous coordinate is exactly 1.
-  warped = (R @ points[..., None])[..., 0] + p
-  return warped / torch.ones_like(warped[..., :1])
+  warped = points
+  if spec.warp_use_pivot:                               # warping.py:339-342
+    pivot = dense(params['branches_p']['logit'], trunk_output)
+    warped = warped + pivot
+  warped = (R @ warped[..., None])[..., 0] + p
+  warped = warped / torch.ones_like(warped[..., :1])
+  if spec.warp_use_pivot:                               # warping.py:347-348
+    warped = warped - pivot
+  if spec.warp_use_translation:                         # warping.py:350-352
+    warped = warped + dense(params['branches_t']['logit'], trunk_output)
+  return warped
 
 
 def translation_field_warp(params, spec, points, metadata_embed, alpha):
@@ -294,15 +328,34 @@ def glo_encode(params: Dict[str, Any], ids: Tensor) -> Tensor:
   return params['embed']['embedding'][ids.long()]
 
 
+def encode_warp_metadata(params, spec: OracleSpec, metadata: Tensor,
+                         time_alpha: Optional[float], dtype) -> Tensor:
+  """encode_metadata of TranslationField (warping.py:125-141) / SE3Field
+  (warping.py:309-320)."""
+  kind = spec.warp_metadata_encoder_type
+  F = spec.metadata_encoder_num_freqs
+  if kind == 'glo':
+    return glo_encode(params['metadata_encoder'], metadata)
+  if kind == 'time':
+    return time_encode(params['metadata_encoder'], F, metadata, time_alpha, dtype)
+  if kind == 'blend' and spec.warp_field_type == 'translation':
+    glo_embed = glo_encode(params['glo_encoder'], metadata).to(dtype)
+    # self.time_encoder(metadata): the integer ids themselves, alpha=None
+    time_embed = time_encode(params['time_encoder'], F, metadata.to(dtype), None, dtype)
+    return (1.0 - time_alpha) * glo_embed + time_alpha * time_embed
+  raise ValueError(f'Unknown metadata encoder type {kind!r}')
+
+
 def warp_field_apply(params, spec: OracleSpec, points: Tensor,
                      metadata: Tensor, alpha: float,
-                     metadata_encoded: bool = False) -> Tensor:
+                     metadata_encoded: bool = False,
+                     time_alpha: Optional[float] = None) -> Tensor:
   """SE3Field.__call__ / TranslationField.__call__ without the Jacobian
   (warping.py:355-389, 160-199)."""
   if metadata_encoded:
     embed = metadata
   else:
-    embed = glo_encode(params['metadata_encoder'], metadata)
+    embed = encode_warp_metadata(params, spec, metadata, time_alpha, points.dtype)
   if spec.warp_field_type == 'se3':
     return se3_field_warp(params, spec, points, embed, alpha)
   if spec.warp_field_type == 'translation':
@@ -469,23 +522,28 @@ def get_condition_inputs(params, spec: OracleSpec, viewdirs: Tensor,
 
 def render_samples(params, spec: OracleSpec, level: str, points, z_vals,
                    directions, viewdirs, metadata, warp_alpha, use_warp=True,
-                   metadata_encoded=False, return_points=False):
-  """models.py:230-287 (noise_regularize is a no-op on the deterministic path,
-  model_utils.py:266-282)."""
+                   metadata_encoded=False, return_points=False,
+                   time_alpha=None):
+  """models.py:230-287.  noise_regularize (model_utils.py:266-282) is a no-op
+  whenever it can run: with noise_std > 0 and stratified sampling the reference
+  indexes the NerfMLP's output DICT as an array (models.py:272-275 hands
+  {'rgb','alpha'} to raw[..., 3:4]) and raises, so there is no behaviour to restate."""
   trunk_c, alpha_c, rgb_c = get_condition_inputs(
       params, spec, viewdirs, metadata, metadata_encoded)
   out = {}
   if return_points:
     out['points'] = points
   if use_warp:
-    warp_meta = metadata['warp']
+    # models.py:252-254
+    warp_meta = (metadata['time'] if spec.warp_metadata_encoder_type == 'time'
+                 else metadata['warp'])
     if metadata_encoded:
       warp_meta = warp_meta[:, None, :].expand(*points.shape[:2],
                                                 spec.num_warp_features)
     else:
       warp_meta = warp_meta[:, None, :].expand(*points.shape[:2], 1)
     points = warp_field_apply(params['warp_field'], spec, points, warp_meta,
-                              warp_alpha, metadata_encoded)
+                              warp_alpha, metadata_encoded, time_alpha)
     if return_points:
       out['warped_points'] = points
   points_embed = sinusoidal_encode(points, spec.num_nerf_point_freqs)
@@ -509,7 +567,8 @@ def render_forward(params, spec: OracleSpec, rays_dict: Dict[str, Any],
                    metadata_encoded: bool = False, return_points: bool = False,
                    t_rand: Optional[Tensor] = None,
                    u_rand: Optional[Tensor] = None,
-                   dtype=torch.float32) -> Dict[str, Dict[str, Tensor]]:
+                   dtype=torch.float32, time_alpha: Optional[float] = None
+                   ) -> Dict[str, Dict[str, Tensor]]:
   """NerfModel.__call__ (models.py:289-375), deterministic unless the caller
   supplies the uniform draws `t_rand` (B,Nc) / `u_rand` (B,Nf) that stand in
   for jax.random.  Always returns weights plus per-sample diagnostics."""
@@ -525,7 +584,7 @@ def render_forward(params, spec: OracleSpec, rays_dict: Dict[str, Any],
       spec.use_linear_disparity, t_rand)
   coarse = render_samples(params, spec, 'coarse', points, z_vals, directions,
                           viewdirs, metadata, warp_alpha, use_warp,
-                          metadata_encoded, return_points)
+                          metadata_encoded, return_points, time_alpha)
   coarse['z_vals'] = z_vals
   out = {'coarse': coarse}
   if spec.num_fine_samples > 0:
@@ -535,7 +594,7 @@ def render_forward(params, spec: OracleSpec, rays_dict: Dict[str, Any],
                                 u_rand)
     fine = render_samples(params, spec, 'fine', points, z_fine, directions,
                           viewdirs, metadata, warp_alpha, use_warp,
-                          metadata_encoded, return_points)
+                          metadata_encoded, return_points, time_alpha)
     fine['z_vals'] = z_fine
     out['fine'] = fine
   return out
@@ -544,7 +603,8 @@ def render_forward(params, spec: OracleSpec, rays_dict: Dict[str, Any],
 def render_level(params, spec: OracleSpec, level: str,
                  rays_dict: Dict[str, Any], z_vals: Tensor,
                  warp_alpha: float = 0.0, use_warp: bool = True,
-                 dtype=torch.float32, metadata_encoded: bool = False) -> Dict[str, Tensor]:
+                 dtype=torch.float32, metadata_encoded: bool = False,
+                 time_alpha: Optional[float] = None) -> Dict[str, Tensor]:
   """One level of NerfModel.__call__ for caller-supplied z_vals: points =
   o + z d (model_utils.py:72-73 / :214-215) then render_samples
   (models.py:230-287).  Used to test the levels in isolation."""
@@ -556,7 +616,7 @@ def render_level(params, spec: OracleSpec, level: str,
   points = origins[:, None, :] + z_vals[:, :, None] * directions[:, None, :]
   out = render_samples(tree_to(params, dtype), spec, level, points, z_vals,
                        directions, viewdirs, rays_dict.get('metadata', {}),
-                       warp_alpha, use_warp, metadata_encoded, True)
+                       warp_alpha, use_warp, metadata_encoded, True, time_alpha)
   out['z_vals'] = z_vals
   return out
 
@@ -648,8 +708,18 @@ def init_params(spec: OracleSpec, seed: int = 0) -> Dict[str, Any]:
   params = {}
   if spec.use_warp:
     dw = 3 + 6 * spec.num_warp_freqs + spec.num_warp_features
-    wf = {'metadata_encoder': {'embed': {'embedding': _uniform(
-        gen, (spec.num_warp_embeddings, spec.num_warp_features), 0.05)}}}
+    glo = lambda: {'embed': {'embedding': _uniform(
+        gen, (spec.num_warp_embeddings, spec.num_warp_features), 0.05)}}
+    tenc = lambda: {'mlp': _mlp_init(
+        gen, 1 + 2 * spec.metadata_encoder_num_freqs, TIME_ENCODER_DEPTH,
+        TIME_ENCODER_WIDTH, TIME_ENCODER_SKIPS, spec.num_warp_features,
+        'uniform', 0.05)}
+    if spec.warp_metadata_encoder_type == 'glo':
+      wf = {'metadata_encoder': glo()}
+    elif spec.warp_metadata_encoder_type == 'time':
+      wf = {'metadata_encoder': tenc()}
+    else:
+      wf = {'glo_encoder': glo(), 'time_encoder': tenc()}
     if spec.warp_field_type == 'se3':
       wf['trunk'] = _mlp_init(gen, dw, spec.warp_trunk_depth,
                               spec.warp_trunk_width, spec.warp_skips)
@@ -657,6 +727,12 @@ def init_params(spec: OracleSpec, seed: int = 0) -> Dict[str, Any]:
           gen, spec.warp_trunk_width, 3, 'uniform', 1e-4)}
       wf['branches_v'] = {'logit': _dense_init(
           gen, spec.warp_trunk_width, 3, 'uniform', 1e-4)}
+      if spec.warp_use_pivot:
+        wf['branches_p'] = {'logit': _dense_init(
+            gen, spec.warp_trunk_width, 3, 'uniform', 1e-4)}
+      if spec.warp_use_translation:
+        wf['branches_t'] = {'logit': _dense_init(
+            gen, spec.warp_trunk_width, 3, 'uniform', 1e-4)}
     else:
       wf['mlp'] = _mlp_init(gen, dw, spec.warp_trunk_depth,
                             spec.warp_trunk_width, spec.warp_skips, 3,

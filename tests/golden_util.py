@@ -11,7 +11,8 @@ from oracle import nerfies_oracle as O
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
 CASES = ['se3_small', 'translation_small', 'nowarp_variants',
          'alpha_cond_init', 'se3_stratified', 'quarterhd_dims',
-         'test_local_dims', 'encoded_small']
+         'test_local_dims', 'encoded_small', 'time_small', 'blend_small',
+         'pivot_small']
 
 
 def unflatten(flat):
@@ -45,12 +46,14 @@ class Golden:
     d['warp_skips'] = tuple(d['warp_skips'])
     self.spec = O.OracleSpec(**d)
     self.warp_alpha = float(z['warp_alpha'])
+    self.time_alpha = float(z['time_alpha']) if 'time_alpha' in z.files else 0.0
     self.rays = {
         'origins': torch.from_numpy(z['rays/origins']),
         'directions': torch.from_numpy(z['rays/directions']),
+        # ids are uint32 in the fixture; metadata['time'] is float32 (models.py:252)
         'metadata': {k.split('/')[-1]: torch.from_numpy(
-            z[k].astype(np.int32)) for k in z.files
-                     if k.startswith('rays/metadata/')},
+            z[k] if z[k].dtype.kind == 'f' else z[k].astype(np.int32))
+                     for k in z.files if k.startswith('rays/metadata/')},
     }
     if 'oracle_param_seed' in z.files:
       p = O.init_params(self.spec, int(z['oracle_param_seed']))
@@ -82,11 +85,15 @@ class Golden:
       }
     self.warp = None
     if 'warp/points' in z.files:
+      ids = z['warp/ids']
       self.warp = {
           'points': torch.from_numpy(z['warp/points']),
-          'ids': torch.from_numpy(z['warp/ids'].astype(np.int32)),
+          'ids': torch.from_numpy(ids if ids.dtype.kind == 'f' else ids.astype(np.int32)),
           'warped_points': torch.from_numpy(z['warp/warped_points']),
       }
+      if 'warp/enc_embed' in z.files:
+        self.warp['enc_embed'] = torch.from_numpy(z['warp/enc_embed'])
+        self.warp['enc_warped_points'] = torch.from_numpy(z['warp/enc_warped_points'])
 
 
 def rel_err(a, b, floor=1e-2):
@@ -103,10 +110,16 @@ def model_from_spec(spec_dict, precision='fp32', device=None, batch_size=64):
   if s['warp_field_type'] == 'se3':
     wk = {'trunk_depth': s['warp_trunk_depth'],
           'trunk_width': s['warp_trunk_width'], 'skips': tuple(s['warp_skips'])}
+    if s.get('warp_use_pivot'):
+      wk['use_pivot'] = True
+    if s.get('warp_use_translation'):
+      wk['use_translation'] = True
   else:
     wk = {'depth': s['warp_trunk_depth'],
           'hidden_channels': s['warp_trunk_width'],
           'skips': tuple(s['warp_skips'])}
+  if s.get('metadata_encoder_num_freqs', 1) != 1:
+    wk['metadata_encoder_num_freqs'] = s['metadata_encoder_num_freqs']
   return nb.NerfModel(
       num_coarse_samples=s['num_coarse_samples'],
       num_fine_samples=s['num_fine_samples'], use_viewdirs=s['use_viewdirs'],
@@ -136,6 +149,7 @@ def model_from_spec(spec_dict, precision='fp32', device=None, batch_size=64):
       use_trunk_condition=s['use_trunk_condition'],
       use_alpha_condition=s['use_alpha_condition'],
       use_rgb_condition=s['use_rgb_condition'], warp_kwargs=wk,
+      warp_metadata_encoder_type=s.get('warp_metadata_encoder_type', 'glo'),
       precision=precision, batch_size=batch_size, device=device)
 
 

@@ -50,12 +50,16 @@ def test_apply_without_gpu_raises():
 class _FakeModel:
   """Stands in for NerfModel on the CPU: a closed-form 'render'."""
 
-  def apply(self, variables, rays, warp_extra=None, rngs=None, mutable=False):
+  def apply(self, variables, rays, warp_extra=None, rngs=None, mutable=False, _packed=False):
     o, d = rays['origins'], rays['directions']
     scale = variables['params']['scale']
     rgb = (o * 2 + d) * scale + warp_extra['alpha']
-    return {'coarse': {'rgb': rgb * 0.5, 'acc': o[:, 0]},
-            'fine': {'rgb': rgb, 'acc': o[:, 0] + d[:, 1]}}
+    pack = lambda rgb, acc: torch.cat([rgb, o[:, 1:2], d[:, 2:3], acc[:, None]], -1)
+    packed = {'coarse': pack(rgb * 0.5, o[:, 0]), 'fine': pack(rgb, o[:, 0] + d[:, 1])}
+    if _packed:          # (n,6) per level: rgb3, depth, med_depth, acc - what NerfModel.apply hands over
+      return packed
+    return {lv: {'rgb': p[:, :3], 'depth': p[:, 3], 'med_depth': p[:, 4], 'acc': p[:, 5]}
+            for lv, p in packed.items()}
 
 
 def _frame(h, w):
@@ -116,6 +120,7 @@ def test_two_rank_render_equals_single_process(tmp_path):
       _state(), rays, evaluation.make_model_fn(_FakeModel()), 1, 0, chunk=7)
   for r in range(2):
     out = torch.load(os.path.join(str(tmp_path), f'out{r}.pt'))
+    assert set(out) == {'rgb', 'depth', 'med_depth', 'acc'}
     for k in single:
       assert torch.equal(out[k], single[k]), (r, k)
 

@@ -25,7 +25,8 @@ OUT_KEYS = ('rgb', 'depth', 'med_depth', 'acc', 'weights')
 def test_coarse_level(name):
   g = Golden(name)
   out = O.render_forward(g.params, g.spec, g.rays, warp_alpha=g.warp_alpha,
-                         return_points=True, t_rand=g.t_rand, u_rand=g.u_rand)
+                         return_points=True, t_rand=g.t_rand, u_rand=g.u_rand,
+                         time_alpha=g.time_alpha)
   for key, ref in g.out['coarse'].items():
     err = rel_err(out['coarse'][key], ref)
     assert err < TOL, f'{name} coarse/{key}: rel err {err:.3e}'
@@ -64,7 +65,7 @@ def test_resample_given_reference_weights(name):
 def test_fine_level_given_reference_z(name):
   g = Golden(name)
   out = O.render_level(g.params, g.spec, 'fine', g.rays,
-                       g.out['fine']['z_vals'], g.warp_alpha)
+                       g.out['fine']['z_vals'], g.warp_alpha, time_alpha=g.time_alpha)
   for key, ref in g.out['fine'].items():
     err = rel_err(out[key], ref)
     assert err < TOL, f'{name} fine/{key}: rel err {err:.3e}'
@@ -74,7 +75,7 @@ def test_fine_level_given_reference_z(name):
 def test_end_to_end(name):
   g = Golden(name)
   out = O.render_forward(g.params, g.spec, g.rays, warp_alpha=g.warp_alpha,
-                         t_rand=g.t_rand, u_rand=g.u_rand)
+                         t_rand=g.t_rand, u_rand=g.u_rand, time_alpha=g.time_alpha)
   for key in ('rgb', 'depth', 'acc'):
     err = rel_err(out['fine'][key], g.out['fine'][key], floor=1e-2)
     assert err < TOL_E2E_RGB, f'{name} fine/{key}: rel err {err:.3e}'
@@ -84,9 +85,14 @@ def test_end_to_end(name):
 def test_warp_field_apply(name):
   g = Golden(name)
   got = O.warp_field_apply(g.params['warp_field'], g.spec, g.warp['points'],
-                           g.warp['ids'], g.warp_alpha)
+                           g.warp['ids'], g.warp_alpha, time_alpha=g.time_alpha)
   err = rel_err(got, g.warp['warped_points'])
   assert err < TOL, f'{name}: rel err {err:.3e}'
+  # warp_field.apply(..., metadata_encoded=True) (warping.py:186-187, 378)
+  got = O.warp_field_apply(g.params['warp_field'], g.spec, g.warp['points'],
+                           g.warp['enc_embed'], g.warp_alpha, metadata_encoded=True)
+  err = rel_err(got, g.warp['enc_warped_points'])
+  assert err < TOL, f'{name} (metadata_encoded): rel err {err:.3e}'
 
 
 def test_fp64_shadow_close_to_fp32():

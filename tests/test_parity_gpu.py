@@ -34,7 +34,7 @@ def _write_report():
 DEV = 'cuda:0'
 
 
-def _render_level(model, params, level, rays, z, alpha, use_warp=True):
+def _render_level(model, params, level, rays, z, alpha, use_warp=True, time_alpha=0.0):
   """nfb_render_samples through the C ABI."""
   from nerfies_b200 import _lib
   from nerfies_b200.models import _prep_f32, _prep_ids, _ptr, _stream
@@ -46,6 +46,9 @@ def _render_level(model, params, level, rays, z, alpha, use_warp=True):
   d = _prep_f32(rays['directions'], dev)
   md = rays.get('metadata', {})
   ids = [_prep_ids(md.get(k), dev) for k in ('warp', 'appearance', 'camera')]
+  if model.use_warp and model.warp_metadata_encoder_type == 'time':
+    ids[0] = _prep_f32(md['time'], dev).reshape(-1)      # metadata['time'] (models.py:252-254)
+  model._set_time_alpha(hd, time_alpha)
   zc = _prep_f32(z, dev)
   out = torch.empty(B, 6, device=dev)
   w = torch.empty(B, S, device=dev)
@@ -72,10 +75,25 @@ def _check_level(name, level, got, ref, z, use_warp):
   assert med_depth_ok(got['med_depth'], ref, z), f'{name} {level}/med_depth'
 
 
+def _golden_model(g, precision):
+  """The tcgen05 modes cover the gin-file widths (trunk 256, warp/rgb 128, relu, rgb
+  condition only); for the small fixtures they refuse loudly - skip those."""
+  from nerfies_b200 import _lib
+  model = model_from_spec(g.spec_dict, device=DEV, precision=precision)
+  if precision != 'fp32':
+    try:
+      model.handle(64)
+    except _lib.NfbError as e:
+      assert 'use precision fp32' in str(e)
+      pytest.skip(f'{g.name}: not a tcgen05 shape ({e})')
+  return model
+
+
+@pytest.mark.parametrize('precision', ['fp32', 'fp16x3'])
 @pytest.mark.parametrize('name', CASES)
-def test_coarse_level_vs_reference_source(name):
+def test_coarse_level_vs_reference_source(name, precision):
   g = Golden(name)
-  model = model_from_spec(g.spec_dict, device=DEV)
+  model = _golden_model(g, precision)
   params = tree_to_device(g.params, DEV)
   z = g.out['coarse'].get('z_vals')
   if z is None:
@@ -83,17 +101,18 @@ def test_coarse_level_vs_reference_source(name):
                                g.spec.num_coarse_samples, g.spec.near,
                                g.spec.far, g.spec.use_linear_disparity,
                                g.t_rand)
-  got = _render_level(model, params, 0, g.rays, z, g.warp_alpha)
+  got = _render_level(model, params, 0, g.rays, z, g.warp_alpha, time_alpha=g.time_alpha)
   _check_level(name, 'coarse', got, g.out['coarse'], z, g.spec.use_warp)
 
 
+@pytest.mark.parametrize('precision', ['fp32', 'fp16x3'])
 @pytest.mark.parametrize('name', CASES)
-def test_fine_level_given_reference_z(name):
+def test_fine_level_given_reference_z(name, precision):
   g = Golden(name)
-  model = model_from_spec(g.spec_dict, device=DEV)
+  model = _golden_model(g, precision)
   params = tree_to_device(g.params, DEV)
   z = g.out['fine']['z_vals']
-  got = _render_level(model, params, 1, g.rays, z, g.warp_alpha)
+  got = _render_level(model, params, 1, g.rays, z, g.warp_alpha, time_alpha=g.time_alpha)
   _check_level(name, 'fine', got, g.out['fine'], z, g.spec.use_warp)
 
 
@@ -166,19 +185,21 @@ def _e2e_tol(g, key, encoded=False):
     rays = dict(g.rays, metadata=g.enc['metadata']) if encoded else g.rays
     ref = (g.enc['out'] if encoded else g.out)['fine']
     o64 = O.render_forward(g.params, g.spec, rays, warp_alpha=g.warp_alpha, metadata_encoded=encoded,
-                           t_rand=g.t_rand, u_rand=g.u_rand, dtype=torch.float64)['fine']
+                           t_rand=g.t_rand, u_rand=g.u_rand, dtype=torch.float64,
+                           time_alpha=g.time_alpha)['fine']
     _E2E_BAND[ck] = {k: rel_err(o64[k], ref[k]) for k in ('rgb', 'depth', 'acc')}
   return max(TOL_E2E, 3.0 * _E2E_BAND[ck][key])
 
 
+@pytest.mark.parametrize('precision', ['fp32', 'fp16x3'])
 @pytest.mark.parametrize('name', CASES)
-def test_end_to_end_apply(name):
+def test_end_to_end_apply(name, precision):
   g = Golden(name)
-  model = model_from_spec(g.spec_dict, device=DEV)
+  model = _golden_model(g, precision)
   params = tree_to_device(g.params, DEV)
   for return_points in (False, True):
     out = model.apply({'params': params}, g.rays,
-                      warp_extra={'alpha': g.warp_alpha, 'time_alpha': 0.0},
+                      warp_extra={'alpha': g.warp_alpha, 'time_alpha': g.time_alpha},
                       return_weights=True, return_points=return_points,
                       t_rand=g.t_rand, u_rand=g.u_rand)
     torch.cuda.synchronize()
@@ -186,6 +207,8 @@ def test_end_to_end_apply(name):
       assert rel_err(out['coarse'][k].cpu(), g.out['coarse'][k]) < TOL
     for k in ('rgb', 'depth', 'acc'):
       err = rel_err(out['fine'][k].cpu(), g.out['fine'][k])
+      if not return_points:    # measured (not only bounded) end-to-end error per fixture -> the report
+        _REPORT.append((f'{name}[{precision}] e2e vs fixture', 'fine', k, err, _e2e_tol(g, k)))
       assert err < _e2e_tol(g, k), f'{name} fine/{k}: {err:.3e} (tol {_e2e_tol(g, k):.1e})'
     if return_points:
       assert rel_err(out['coarse']['points'].cpu(),
@@ -193,17 +216,35 @@ def test_end_to_end_apply(name):
       assert out['fine']['points'].shape == g.out['fine']['points'].shape
 
 
+@pytest.mark.parametrize('precision', ['fp32', 'fp16x3'])
 @pytest.mark.parametrize('name', [c for c in CASES if c != 'nowarp_variants'])
-def test_warp_forward(name):
+def test_warp_forward(name, precision):
   g = Golden(name)
-  model = model_from_spec(g.spec_dict, device=DEV)
+  model = _golden_model(g, precision)
   wf = model.create_warp_field(model, num_batch_dims=1)
   out = wf.apply({'params': tree_to_device(g.params, DEV)}, g.warp['points'],
-                 g.warp['ids'], {'alpha': g.warp_alpha, 'time_alpha': 0.0},
+                 g.warp['ids'], {'alpha': g.warp_alpha, 'time_alpha': g.time_alpha},
                  False, False)
   torch.cuda.synchronize()
   err = rel_err(out['warped_points'].cpu(), g.warp['warped_points'])
   assert err < TOL, f'{name}: {err:.3e}'
+  # the reference call site passes the warp subtree only (training.py:127-131), and
+  # metadata_encoded=True takes per-point embeddings (warping.py:186-187, 378)
+  sub = {'params': tree_to_device(g.params, DEV)['warp_field']}
+  out = wf.apply(sub, g.warp['points'], g.warp['enc_embed'],
+                 {'alpha': g.warp_alpha, 'time_alpha': g.time_alpha}, False, True)
+  torch.cuda.synchronize()
+  err = rel_err(out['warped_points'].cpu(), g.warp['enc_warped_points'])
+  assert err < TOL, f'{name} (metadata_encoded, warp subtree): {err:.3e}'
+  # a changed warp subtree must take effect (no stale cached weights)
+  import copy
+  p2 = copy.deepcopy(g.params['warp_field'])
+  head = 'branches_v' if g.spec.warp_field_type == 'se3' else 'mlp'
+  p2[head]['logit']['bias'] = p2[head]['logit']['bias'] + 0.25
+  out2 = wf.apply({'params': tree_to_device(p2, DEV)}, g.warp['points'], g.warp['enc_embed'],
+                  {'alpha': g.warp_alpha, 'time_alpha': g.time_alpha}, False, True)
+  torch.cuda.synchronize()
+  assert float((out2['warped_points'] - out['warped_points']).abs().max()) > 1e-2
 
 
 def test_metadata_encoded_apply():
@@ -324,14 +365,22 @@ def test_levels_vs_oracle(dims, precision):
 # ---------------------------------------------------------------------------
 # Size-independent properties at the benchmark's full size.
 # ---------------------------------------------------------------------------
-def test_full_size_properties():
+# (max-rel coarse, max-rel fine on the oracle's z, max-rel end to end, PSNR dB) per mode: the
+# bounds bench.py states for the rays it times.
+_MODE_BOUNDS = {'fp32': (1e-4, 1e-4, 2e-3, 70.0), 'fp16x3': (1e-4, 1e-4, 2e-3, 70.0),
+                'bf16': (8e-2, 8e-2, 1.5e-1, 35.0)}
+
+
+@pytest.mark.parametrize('precision', ['fp32', 'fp16x3', 'bf16'])
+def test_full_size_properties(precision):
   spec = O.OracleSpec(num_coarse_samples=128, num_fine_samples=128, near=0.02,
                       far=0.83, num_nerf_point_freqs=8,
                       sigma_activation='softplus', use_warp=True,
                       use_appearance_metadata=True, num_warp_embeddings=200,
                       num_appearance_embeddings=200)
   B = 8192
-  p, rays, model = _oracle_case(spec, B, 9, 8.0)
+  p, rays, model = _oracle_case(spec, B, 9, 8.0, precision)
+  rays_cpu = rays
   pg = tree_to_device(p, DEV)
   rays = {'origins': rays['origins'].to(DEV),
           'directions': rays['directions'].to(DEV),
@@ -366,6 +415,25 @@ def test_full_size_properties():
   zc = out['coarse']['z_vals']
   idx = torch.searchsorted(z.contiguous(), zc.contiguous())
   assert torch.equal(torch.gather(z, 1, idx.clamp(max=z.shape[1] - 1)), zc)
+  # a sample of the 8192 rays against the oracle (every 64th ray: rays from every
+  # part of the grid), in this mode's stated bounds.
+  pick = torch.arange(0, B, 64)
+  sub_cpu = {'origins': rays_cpu['origins'][pick], 'directions': rays_cpu['directions'][pick],
+             'metadata': {k: v[pick] for k, v in rays_cpu['metadata'].items()}}
+  ref = O.render_forward(p, spec, sub_cpu, warp_alpha=8.0, return_points=True)
+  b_coarse, b_fz, b_e2e, b_psnr = _MODE_BOUNDS[precision]
+  for k in ('rgb', 'depth', 'acc', 'weights'):
+    err = rel_err(out['coarse'][k][pick.to(DEV)].cpu(), ref['coarse'][k])
+    assert err < b_coarse, f'[{precision}] coarse/{k} of the full-size batch: {err:.3e}'
+  for k in ('rgb', 'depth', 'acc'):
+    err = rel_err(out['fine'][k][pick.to(DEV)].cpu(), ref['fine'][k])
+    assert err < b_e2e, f'[{precision}] e2e fine/{k} of the full-size batch: {err:.3e}'
+  mse = float(((out['fine']['rgb'][pick.to(DEV)].cpu() - ref['fine']['rgb'])**2).mean())
+  assert -10 * np.log10(max(mse, 1e-20)) > b_psnr
+  got = _render_level(model, pg, 1, sub_cpu, ref['fine']['z_vals'], 8.0)
+  for k in ('rgb', 'depth', 'acc', 'weights', 'warped_points'):
+    err = rel_err(got[k], ref['fine'][k])
+    assert err < b_fz, f'[{precision}] fine/{k} on the oracle z: {err:.3e}'
 
 
 def test_host_entry_point_matches_device_path():

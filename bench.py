@@ -54,6 +54,12 @@ WORKLOADS = {
     'fullhd-train': dict(
         rays=4096, nc=256, nf=256, fp=10, fw=8, app=True, cam=False, flop=1382400,
         desc='gpu_fullhd.gin training batch: {B} rays x (256+256) samples, num_nerf_point_freqs=10'),
+    'eval-1080p': dict(
+        rays=1920 * 1080, nc=256, nf=256, fp=10, fw=8, app=True, cam=False, flop=1382400,
+        frame=(1920, 1080),
+        desc='eval.py render path: one full 1920x1080 frame = {B} rays x (256+256) samples, '
+             'gpu_fullhd.gin model dims, rays generated on the GPU per rank, frame split over '
+             'the ranks, one all_gather of 24 B/ray'),
     'fullhd-65536': dict(
         rays=65536, nc=256, nf=256, fp=10, fw=8, app=True, cam=False, flop=1382400,
         desc='gpu_fullhd.gin model dims at {B} rays x (256+256) samples'),
@@ -492,6 +498,97 @@ def roofline(res, wl, B, peaks, precision):
   return r
 
 
+def measure_eval_frame(args, wl, precision, ctx, steps):
+  """BASELINE.json's fifth config (eval.py:330-353): a full frame, rays split
+  1 -> N GPUs, forward only.  A step = one frame through
+  nerfies_b200.evaluation.render_frame; the collective's time is reported.
+  Returns the JSON line (rank 0) or None."""
+  import numpy as np
+  import torch
+  import torch.distributed as dist
+  import nerfies_b200 as nb
+  from nerfies_b200 import evaluation
+  dev, world, rank = ctx['dev'], ctx['world'], ctx['rank']
+  w, h = wl['frame']
+  evals = 2 * wl['nc'] + wl['nf']
+  max_rays = 32768
+  model, params = nb.construct_nerf(0, model_config(wl), max_rays, range(N_IDS), range(2),
+                                    range(N_IDS), NEAR, FAR, precision=precision, device=dev)
+  cpu = lambda t: ({k: cpu(v) for k, v in t.items()} if isinstance(t, dict) else t.cpu())
+  gpu = lambda t: ({k: gpu(v) for k, v in t.items()} if isinstance(t, dict) else t.to(dev))
+  params_cpu = trained_like(cpu(params), seed=1)
+  params = gpu(params_cpu)
+  th = 0.2
+  R = np.array([[np.cos(th), 0, np.sin(th)], [0, 1, 0], [-np.sin(th), 0, np.cos(th)]], np.float32)
+  cam = nb.camera.Camera(orientation=R, position=[0.05, -0.02, -0.35], focal_length=1500.0,
+                         principal_point=[w / 2, h / 2], image_size=[w, h],
+                         radial_distortion=[0.02, -0.01, 0.0], tangential_distortion=[1e-3, -5e-4])
+  md = {'warp': 17, 'appearance': 23}
+  extra = {'alpha': float(wl['fw']), 'time_alpha': 0.0}
+
+  def barrier():
+    if world > 1:
+      dist.barrier()
+    torch.cuda.synchronize()
+
+  frame = evaluation.render_frame(model, params, cam, extra, md, max_rays=max_rays)   # warm-up
+  barrier()
+  sampler = ClockSampler(ctx['local_rank'])
+  sampler.start()
+  launches0 = model.kernel_launches()
+  tms = []
+  for _ in range(steps):
+    t = {}
+    frame = evaluation.render_frame(model, params, cam, extra, md, max_rays=max_rays, timings=t)
+    tms.append((t['render_ms'], t['gather_ms']))
+  barrier()
+  clocks = sampler.stop()
+  launches = model.kernel_launches() - launches0
+  tot = torch.tensor([sum(a + b for a, b in tms), sum(b for _, b in tms)], device=dev, dtype=torch.float64)
+  if world > 1:
+    dist.all_reduce(tot, op=dist.ReduceOp.MAX)
+  ms = float(tot[0]) / steps
+  gather_ms = float(tot[1]) / steps
+  if rank != 0:
+    return None
+  value = w * h * evals / (ms * 1e-3)
+  line = {
+      'metric': 'ray-samples/sec (coarse+fine, device-timed)', 'value': value,
+      'unit': 'ray-samples/s', 'n_gpus': world, 'steps': steps, 'warmup': 1,
+      'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,
+      'dtype': DTYPE_NAMES[precision], 'data': 'synthetic',
+      'config': {'workload': workload_text(wl, w * h), 'workload_name': 'eval-1080p',
+                 'precision': precision, 'rays_per_gpu': -(-w * h // world),
+                 'parallelism': f'frame rows split x{world}; one NCCL all_gather of the packed (rays, 6) result',
+                 'l2': 'a frame is 2.07 M rays: every launch streams far more than L2',
+                 'timing': 'CUDA events on the launch stream around each frame (ray generation + render + '
+                           'all_gather), max over ranks'},
+      'frame_ms': ms, 'all_gather_ms': gather_ms, 'clocks': clocks, 'gpu_launches': int(launches),
+  }
+  if not args.no_parity:
+    # a sample of the frame's pixels against the oracle, on the rays the GPU generated
+    from oracle import nerfies_oracle as O
+    from nerfies_b200 import camera as camera_lib
+    spec = oracle_spec(wl)
+    idx = torch.linspace(0, w * h - 1, 96).round().long()
+    rays = camera_lib.camera_to_rays(cam, dev)
+    sub = {'origins': rays['origins'].reshape(-1, 3)[idx.to(dev)].cpu(),
+           'directions': rays['directions'].reshape(-1, 3)[idx.to(dev)].cpu(),
+           'metadata': {k: torch.full((96, 1), v, dtype=torch.int32) for k, v in md.items()}}
+    torch.set_num_threads(min(16, os.cpu_count() or 1))
+    with torch.no_grad():
+      ref = O.render_forward(params_cpu, spec, sub, warp_alpha=extra['alpha'])
+    got = {k: frame[k].reshape((w * h,) + tuple(frame[k].shape[2:]))[idx.to(dev)].cpu() for k in ('rgb', 'depth', 'acc')}
+    par = {f'max_rel_{k}': rel_err(got[k], ref['fine'][k]) for k in ('rgb', 'depth', 'acc')}
+    par['psnr_db'] = psnr_db(got['rgb'], ref['fine']['rgb'])
+    b = PARITY_BOUNDS[precision]
+    par['bounds'] = {'e2e': b['e2e'], 'psnr_db': b['psnr_db']}
+    par['ok'] = bool(max(par[f'max_rel_{k}'] for k in ('rgb', 'depth', 'acc')) < b['e2e'] and par['psnr_db'] > b['psnr_db'])
+    par['pixels'] = 96
+    line['parity'] = par
+  return line
+
+
 def run_b200(args):
   import torch
   import torch.distributed as dist
@@ -519,6 +616,13 @@ def run_b200(args):
       dist.barrier()
     torch.cuda.synchronize()
 
+  if 'frame' in wl:
+    line = measure_eval_frame(args, wl, precision, ctx, args.steps)
+    if rank == 0:
+      emit(line)
+    if world > 1:
+      dist.destroy_process_group()
+    return
   main = measure(precision, wl, B, args, ctx, want_parity=not args.no_parity)
 
   # End to end through the C ABI's host entry point: host buffers in, host
@@ -554,6 +658,17 @@ def run_b200(args):
       # strong scaling beside the weak headline: the same TOTAL batch split over the ranks
       r = measure(precision, wl, max(1, total_rays // world), args, ctx, want_parity=False)
       also['strong'] = r
+    if args.workload == 'northstar':
+      # BASELINE.json's eval config rides along (one warm-up + one timed 1080p frame), so that the
+      # driver's 1 -> 8 GPU runs record the frame-time curve too; never allowed to break the line
+      try:
+        ev = measure_eval_frame(args, WORKLOADS['eval-1080p'], precision, ctx, 1)
+        if ev is not None:
+          also['eval_1080p'] = {k: ev[k] for k in ('value', 'frame_ms', 'all_gather_ms', 'n_gpus', 'parity')
+                                if k in ev}
+          also['eval_1080p']['workload'] = ev['config']['workload']
+      except Exception as e:   # pylint: disable=broad-except
+        also['eval_1080p'] = {'error': repr(e)}
 
   if rank != 0:
     if world > 1:
@@ -596,7 +711,9 @@ def run_b200(args):
   if also:
     line['also'] = {}
     for name, r in also.items():
-      if name == 'strong':
+      if name == 'eval_1080p':
+        line['also'][name] = r
+      elif name == 'strong':
         b2 = max(1, total_rays // world)
         line['also']['strong_scaling'] = {
             'precision': precision, 'total_rays': b2 * world, 'rays_per_gpu': b2,

@@ -22,7 +22,12 @@
  *    memory), the kernel drains, and the _host entry point / every later call
  *    returns an error ("a tcgen05 kernel aborted ..."); results of that launch
  *    are invalid;
- *  - a handle is not thread-safe: one handle per GPU per process/rank.
+ *  - a handle is not thread-safe: one handle per GPU per process/rank.  Its workspace
+ *    is shared by its calls: consecutive calls on one stream are ordered by the
+ *    stream; when a call arrives on a different stream than the previous one the
+ *    library makes the new stream wait for the previous call's work (one event).
+ *    Concurrent launches from one handle on two streams are therefore serialised,
+ *    not run in parallel - use one handle per stream for that.
  */
 #ifndef NERFIES_B200_H_
 #define NERFIES_B200_H_

@@ -973,6 +973,8 @@ inline int build_tc_program(nfb_handle* h, int level, long long* wbytes, long lo
     const bool last_of_pair = (i == tp.n_units - 1) || (tp.steps[u.step].epi == kEpiWarpHeads && (u.flags & kUStepEnd));
     const uint32_t nf = (i + 1 < tp.n_units) ? tp.units[i + 1].flags : (uint32_t)kUWaitX0;
     u.probe_next = ((nf & kUWaitX0) ? 2u : 0u) | ((nf & kUWaitX1) ? 4u : 0u) | ((nf & kUWaitX2) ? 8u : 0u);
+    // fp16x3: W_lo follows W_hi inside the weight slot, chunk_n rows x 128 B further (in 16-byte units)
+    if (x3) u.probe_next |= (uint32_t)(tp.steps[u.step].chunk_n * (kRowBytes >> 4)) << 16;
     (void)last_of_pair;
   }
   return 0;

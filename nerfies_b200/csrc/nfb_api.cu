@@ -351,11 +351,20 @@ int run_cond(nfb_handle* h, int B, const float* viewdirs, const unsigned* warp_i
   return 0;
 }
 
+// The fp16x3 kernel can finish a ray on chip (volumetric rendering fused into its rgb epilogue)
+// when a ray's samples are whole 128-row tiles.
+bool can_fuse_composite(const nfb_handle* h, int S) {
+  return h->cfg.precision == NFB_PREC_FP16X3 && S % 128 == 0 && S <= nfb::kMaxSamples;
+}
+
 int run_field(nfb_handle* h, int level, long long rows, int S, const float* origins,
               const float* directions, const float* z, float* samples, float* warped,
-              bool use_warp, bool warp_only, cudaStream_t s) {
+              bool use_warp, bool warp_only, cudaStream_t s, float* ray_out = nullptr,
+              float* ray_weights = nullptr) {
   if (rows == 0) return 0;
   nfb::FieldArgs a{};
+  a.ray_out = ray_out; a.ray_weights = ray_weights;
+  a.white_bg = h->cfg.use_white_background; a.sample_at_infinity = h->cfg.use_sample_at_infinity;
   a.params = h->d_packed; a.origins = origins; a.directions = directions; a.z_vals = z;
   a.cond = h->d_cond; a.window = h->d_window; a.samples = samples; a.warped = warped;
   a.num_rows = rows; a.samples_per_ray = S; a.use_warp = use_warp; a.warp_only = warp_only;
@@ -821,19 +830,28 @@ int nfb_render_forward(nfb_handle* h, int B, const float* origins, const float* 
                (flags & NFB_FLAG_METADATA_ENCODED) != 0)) return -1;
   // coarse level (models.py:332-349)
   if (nfb_coarse_z_vals(h, B, t_rand, h->d_zc, stream)) return -1;
-  if (run_field(h, 0, (long long)B * nc, nc, origins, directions, h->d_zc, h->d_samples, nullptr,
-                use_warp, false, s)) return -1;
   float* wc = w_coarse ? w_coarse : h->d_wc;
-  if (run_composite(h, B, nc, h->d_samples, h->d_zc, directions,
-                    out_coarse ? out_coarse : h->d_out_c, wc, s)) return -1;
+  float* oc = out_coarse ? out_coarse : h->d_out_c;
+  if (can_fuse_composite(h, nc)) {
+    // field + volumetric rendering in one kernel: 24 B per ray (+ the coarse weights) leave the SM
+    if (run_field(h, 0, (long long)B * nc, nc, origins, directions, h->d_zc, nullptr, nullptr,
+                  use_warp, false, s, oc, wc)) return -1;
+  } else {
+    if (run_field(h, 0, (long long)B * nc, nc, origins, directions, h->d_zc, h->d_samples, nullptr,
+                  use_warp, false, s)) return -1;
+    if (run_composite(h, B, nc, h->d_samples, h->d_zc, directions, oc, wc, s)) return -1;
+  }
   if (!fine) return 0;
   // hierarchical resampling + fine level (models.py:352-370)
   float* zf = z_fine ? z_fine : h->d_zf;
   if (run_resample(h, B, h->d_zc, wc, u_rand, zf, s)) return -1;
+  float* of = out_fine ? out_fine : h->d_out_f;
+  if (can_fuse_composite(h, nfine))
+    return run_field(h, 1, (long long)B * nfine, nfine, origins, directions, zf, nullptr, nullptr,
+                     use_warp, false, s, of, w_fine);
   if (run_field(h, 1, (long long)B * nfine, nfine, origins, directions, zf, h->d_samples, nullptr,
                 use_warp, false, s)) return -1;
-  return run_composite(h, B, nfine, h->d_samples, zf, directions,
-                       out_fine ? out_fine : h->d_out_f, w_fine, s);
+  return run_composite(h, B, nfine, h->d_samples, zf, directions, of, w_fine, s);
 }
 
 int nfb_render_forward_host(nfb_handle* h, int B, const float* origins, const float* directions,

@@ -358,7 +358,7 @@ class NerfModel:
   def apply(self, variables, rays_dict, warp_extra=None, metadata_encoded=False,
             use_warp=True, return_points=False, return_weights=False,
             return_warp_jacobian=False, deterministic=False, rngs=None,
-            mutable=False, t_rand=None, u_rand=None):
+            mutable=False, t_rand=None, u_rand=None, _packed=False):
     """model.apply({'params': params}, rays_dict, warp_extra=..., rngs=...)
     as called at training.py:229-237 and eval.py:331-338 (models.py:289-375).
 

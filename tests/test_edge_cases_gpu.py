@@ -19,7 +19,7 @@ def _rays(n, spec, seed):
           'metadata': {k: v.to(DEV) for k, v in r['metadata'].items()}}
 
 
-@pytest.mark.parametrize('precision', ['fp32', 'bf16'])
+@pytest.mark.parametrize('precision', ['fp32', 'bf16', 'fp16x3'])
 def test_empty_and_single_ray(precision):
   spec = O.OracleSpec(num_coarse_samples=128, num_fine_samples=128, near=0.02,
                       far=0.83, num_nerf_point_freqs=8,
@@ -200,3 +200,41 @@ def test_cta_pair_variant_is_bit_identical(monkeypatch):
       for k in ('rgb', 'depth', 'acc', 'warped_points'):
         assert torch.equal(a[lv][k], b[lv][k]), (n, lv, k)
   monkeypatch.delenv('NFB_TC_PAIR', raising=False)
+
+
+@pytest.mark.parametrize('variant', ['default', 'white_bg_no_infinity', 'fullhd_256'])
+def test_fused_composite_matches_the_staged_path(variant):
+  """fp16x3: when a ray is a whole number of 128-sample tiles the field kernel finishes the
+  ray on chip (volumetric rendering fused into its rgb epilogue, model_utils.py:104-136);
+  otherwise - and on the return_points path - samples go through composite_kernel.  Both
+  must agree to fp32 re-association, including the median depth and the two
+  background / infinity variants."""
+  kw = dict(num_coarse_samples=128, num_fine_samples=128)
+  if variant == 'white_bg_no_infinity':
+    kw.update(use_white_background=True, use_sample_at_infinity=False)
+  if variant == 'fullhd_256':
+    kw = dict(num_coarse_samples=256, num_fine_samples=256, num_nerf_point_freqs=10)
+  spec = O.OracleSpec(near=0.02, far=0.83, sigma_activation='softplus', use_warp=True,
+                      use_appearance_metadata=True, num_warp_embeddings=9,
+                      num_appearance_embeddings=9, **{'num_nerf_point_freqs': 8, **kw})
+  p_cpu = O.make_trained_like(O.init_params(spec, 2))
+  p = tree_to_device(p_cpu, DEV)
+  model = model_from_spec(spec_to_dict(spec), precision='fp16x3', device=DEV, batch_size=300)
+  rays = _rays(300, spec, 21)
+  fused = model.apply({'params': p}, rays, warp_extra={'alpha': 6.0}, return_weights=True)
+  staged = model.apply({'params': p}, rays, warp_extra={'alpha': 6.0}, return_weights=True,
+                       return_points=True)
+  torch.cuda.synchronize()
+  for k in ('rgb', 'depth', 'acc', 'weights'):
+    assert rel_err(fused['coarse'][k].cpu(), staged['coarse'][k].cpu()) < 5e-6, k
+  # median depth: identical except where the cumulative weight passes within 1e-5 of 0.5
+  cum = torch.cumsum(staged['coarse']['weights'].double(), -1)
+  near_half = ((cum - 0.5).abs() < 1e-5).any(-1)
+  same = fused['coarse']['med_depth'] == staged['coarse']['med_depth']
+  assert bool((same | near_half).all())
+  # and against the oracle, end to end
+  ref = O.render_forward(p_cpu, spec, {k: (v.cpu() if torch.is_tensor(v) else {a: b.cpu() for a, b in v.items()})
+                                       for k, v in rays.items()}, warp_alpha=6.0)
+  for k in ('rgb', 'depth', 'acc', 'weights'):
+    assert rel_err(fused['coarse'][k].cpu(), ref['coarse'][k]) < 1e-4, k
+  assert rel_err(fused['fine']['rgb'].cpu(), ref['fine']['rgb']) < 2e-3

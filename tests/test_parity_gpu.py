@@ -390,10 +390,21 @@ def test_full_size_properties(precision):
   out2 = model.apply({'params': pg}, rays, warp_extra={'alpha': 8.0},
                      return_weights=True)
   torch.cuda.synchronize()
-  # determinism, and the staged path == the fused entry point, bit for bit.
+  # determinism, and the staged path (field kernel -> composite_kernel) == the one-call entry
+  # point: bit for bit, except in fp16x3 mode where the one-call path finishes the ray inside the
+  # field kernel (warp-shuffle product / sum scans instead of composite_kernel's sequential
+  # scans): same values up to fp32 re-association.
+  out2b = model.apply({'params': pg}, rays, warp_extra={'alpha': 8.0}, return_weights=True)
+  torch.cuda.synchronize()
   for lv in ('coarse', 'fine'):
     for k in ('rgb', 'depth', 'med_depth', 'acc', 'weights'):
-      assert torch.equal(out[lv][k], out2[lv][k]), (lv, k)
+      assert torch.equal(out2[lv][k], out2b[lv][k]), (lv, k)
+      if precision != 'fp16x3':
+        assert torch.equal(out[lv][k], out2[lv][k]), (lv, k)
+      elif lv == 'coarse' and k != 'med_depth':
+        # (the fine level of the two paths sees coarse weights that differ in the last bits, and
+        #  inverse-CDF resampling amplifies that: compared on the coarse level)
+        assert rel_err(out[lv][k].cpu(), out2[lv][k].cpu()) < 5e-6, (lv, k)
   # rays are independent: any sub-batch renders to the same bits.
   sub = slice(1000, 1777)
   rs = {'origins': rays['origins'][sub], 'directions': rays['directions'][sub],

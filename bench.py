@@ -60,6 +60,11 @@ WORKLOADS = {
         desc='eval.py render path: one full 1920x1080 frame = {B} rays x (256+256) samples, '
              'gpu_fullhd.gin model dims, rays generated on the GPU per rank, frame split over '
              'the ranks, one all_gather of 24 B/ray'),
+    'quarterhd-trainstep': dict(
+        rays=6144, nc=128, nf=128, fp=8, fw=8, app=True, cam=False, flop=1370112, trainstep=True,
+        desc='training.train_step on the gpu_quarterhd.gin batch: {B} rays per GPU x (128+128) samples (global '
+             'batch 6144 split over the ranks as the reference does): value_and_grad of the photometric loss '
+             '(fp32, layer-wise tape), ONE NCCL all_reduce of the flat gradient, Adam'),
     'fullhd-65536': dict(
         rays=65536, nc=256, nf=256, fp=10, fw=8, app=True, cam=False, flop=1382400,
         desc='gpu_fullhd.gin model dims at {B} rays x (256+256) samples'),
@@ -589,6 +594,78 @@ def measure_eval_frame(args, wl, precision, ctx, steps):
   return line
 
 
+def measure_train_step(args, wl, ctx):
+  """--workload quarterhd-trainstep: a step = nerfies_b200.training.train_step
+  (value_and_grad + gradient all-reduce + Adam).  The global batch is fixed (the reference's
+  6144 rays) and split over the ranks."""
+  import torch
+  import torch.distributed as dist
+  import nerfies_b200 as nb
+  from nerfies_b200 import training
+  dev, world, rank = ctx['dev'], ctx['world'], ctx['rank']
+  B = max(1, (args.rays or wl['rays']) // world)
+  evals = 2 * wl['nc'] + wl['nf']
+  model, params = nb.construct_nerf(0, model_config(wl), B, range(N_IDS), range(2), range(N_IDS), NEAR, FAR,
+                                    precision='fp32', device=dev)
+  cpu = lambda t: ({k: cpu(v) for k, v in t.items()} if isinstance(t, dict) else t.cpu())
+  gpu = lambda t: ({k: gpu(v) for k, v in t.items()} if isinstance(t, dict) else t.to(dev))
+  state = training.create_train_state(model, gpu(trained_like(cpu(params), seed=1)), warp_alpha=float(wl['fw']))
+  rays = synthetic_rays(B, 1000 + rank, wl)
+  g = torch.Generator().manual_seed(77 + rank)
+  batch = {'origins': rays['origins'].to(dev), 'directions': rays['directions'].to(dev),
+           'metadata': {k: v.to(dev) for k, v in rays['metadata'].items()},
+           'rgb': torch.rand(B, 3, generator=g).to(dev)}
+  sp = training.ScalarParams(learning_rate=1e-3)
+  chunk = 1024
+
+  def barrier():
+    if world > 1:
+      dist.barrier()
+    torch.cuda.synchronize()
+
+  losses = []
+  for _ in range(max(1, min(args.warmup, 2))):
+    state, stats, _ = training.train_step(model, 0, state, batch, sp, chunk_rays=chunk)
+  barrier()
+  sampler = ClockSampler(ctx['local_rank'])
+  sampler.start()
+  tms = []
+  launches0 = model.kernel_launches()
+  barrier()
+  for _ in range(args.steps):
+    t = {}
+    state, stats, _ = training.train_step(model, 0, state, batch, sp, chunk_rays=chunk, timings=t)
+    tms.append(t)
+    losses.append(float(stats['fine']['loss/total']))
+  barrier()
+  clocks = sampler.stop()
+  launches = model.kernel_launches() - launches0
+  keys = ('value_and_grad_ms', 'all_reduce_ms', 'adam_ms')
+  tot = torch.tensor([sum(sum(t[k] for k in keys) for t in tms)] + [sum(t[k] for t in tms) for k in keys],
+                     device=dev, dtype=torch.float64)
+  if world > 1:
+    dist.all_reduce(tot, op=dist.ReduceOp.MAX)
+  if rank != 0:
+    return None
+  ms = float(tot[0]) / args.steps
+  n_params = state.optimizer.flat.numel()
+  return {
+      'metric': 'ray-samples/sec (coarse+fine, device-timed)', 'value': world * B * evals / (ms * 1e-3),
+      'unit': 'ray-samples/s', 'n_gpus': world, 'steps': args.steps, 'warmup': max(1, min(args.warmup, 2)),
+      'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,
+      'dtype': 'fp32 (training tier: layer-wise SIMT GEMMs, forward + backward)', 'data': 'synthetic',
+      'config': {'workload': workload_text(wl, B), 'workload_name': 'quarterhd-trainstep',
+                 'rays_per_gpu': B, 'global_batch': B * world, 'precision': 'fp32',
+                 'parallelism': f'data parallel x{world}: one NCCL all_reduce of the flat gradient '
+                                f'({n_params} fp32 = {n_params * 4 / 1e6:.1f} MB) per step',
+                 'timing': 'CUDA events on the launch stream around the three phases of a step, max over ranks'},
+      'value_and_grad_ms': float(tot[1]) / args.steps, 'all_reduce_ms': float(tot[2]) / args.steps,
+      'adam_ms': float(tot[3]) / args.steps, 'train_flop_per_step': 3 * world * B * evals * wl['flop'],
+      'achieved_tflops_fp32': 3 * world * B * evals * wl['flop'] / (ms * 1e-3) / 1e12 / world,
+      'loss_first_last': [losses[0], losses[-1]], 'clocks': clocks, 'gpu_launches': int(launches),
+  }
+
+
 def run_b200(args):
   import torch
   import torch.distributed as dist
@@ -616,6 +693,13 @@ def run_b200(args):
       dist.barrier()
     torch.cuda.synchronize()
 
+  if wl.get('trainstep'):
+    line = measure_train_step(args, wl, ctx)
+    if rank == 0:
+      emit(line)
+    if world > 1:
+      dist.destroy_process_group()
+    return
   if 'frame' in wl:
     line = measure_eval_frame(args, wl, precision, ctx, args.steps)
     if rank == 0:

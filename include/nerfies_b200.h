@@ -186,6 +186,33 @@ int nfb_warp_forward(nfb_handle* h, int num_points, const float* points,
 /* flags: NFB_FLAG_METADATA_ENCODED = warp_field.apply(..., metadata_encoded=True)
  * (warping.py:186-187, 378): warp_id is (P, num_warp_features) float embeddings. */
 
+/* ---- training tier ----------------------------------------------
+ * jax.value_and_grad of the photometric loss of training.train_step
+ * (training.py:171-175, 214-244, 263-264): loss = mean((rgb_coarse - target)^2) +
+ * mean((rgb_fine - target)^2) over the batch, differentiated w.r.t. every model
+ * parameter through NerfModel.__call__ (z_fine is a constant: lax.stop_gradient,
+ * model_utils.py:211).  fp32, layer-wise with a tape in device memory, hand-written
+ * SIMT GEMMs (csrc/train.cuh); uses the parameters of the last nfb_set_params.
+ *   rgb_target (B,3); chunk_rays: rays per tape chunk (<= 0: 256);
+ *   grads[i]: device tensor of the i-th parameter of nfb_param_info, rows*cols floats,
+ *             ACCUMULATED into (+=): zero them first for a plain gradient;
+ *   loss_out (device, 2 floats): the coarse and the fine loss.
+ * The 'glo' warp metadata encoder only; NFB_FLAG_METADATA_ENCODED is not supported. */
+int nfb_train_value_and_grad(nfb_handle* h, int num_rays, const float* origins,
+                             const float* directions, const float* viewdirs,
+                             const unsigned* warp_id, const unsigned* appearance_id,
+                             const unsigned* camera_id, float warp_alpha,
+                             const float* t_rand, const float* u_rand, unsigned flags,
+                             const float* rgb_target, int chunk_rays, float* const* grads,
+                             const long long* numels, int count, float* loss_out, void* stream);
+
+/* flax.optim.Adam.apply_gradient (training.py:268; beta1 0.9, beta2 0.999, eps 1e-8, no
+ * weight decay are the Flax defaults the reference uses, train.py:219) on flat device
+ * vectors of n floats; `step` counts from 1 (bias correction 1 - beta^step).  No handle. */
+int nfb_adam_step(float* params, const float* grads, float* m, float* v, long long n,
+                  float learning_rate, float beta1, float beta2, float eps, long long step,
+                  void* stream);
+
 /* Measurement aid (bench.py's roofline): when enabled, every launch of the field
  * kernel (the dominant kernel) is bracketed by cudaEvents on its launch stream.
  * nfb_field_time_ms synchronises on the events of the most recent launch of

@@ -18,7 +18,7 @@ SYMBOLS = [
     'nfb_warp_forward', 'nfb_kernel_launches', 'nfb_last_error', 'nfb_version',
     'nfb_set_profiling', 'nfb_field_time_ms', 'nfb_selftest_gemm', 'nfb_set_trace', 'nfb_selftest_microbench',
     'nfb_camera_rays', 'nfb_pixels_to_rays', 'nfb_selftest_gemm2',
-    'nfb_debug_provoke_timeout', 'nfb_set_time_alpha',
+    'nfb_debug_provoke_timeout', 'nfb_set_time_alpha', 'nfb_train_value_and_grad', 'nfb_adam_step',
 ]
 
 ACTIVATIONS = {'none': 0, 'relu': 1, 'elu': 2, 'leaky_relu': 3, 'tanh': 4,
@@ -138,6 +138,11 @@ def load():
   lib.nfb_coarse_z_vals.argtypes = [vp, ci, vp, vp, vp]
   lib.nfb_coarse_z_vals.restype = ci
   lib.nfb_warp_forward.argtypes = [vp, ci, vp, vp, cf, cu, vp, vp]
+  lib.nfb_train_value_and_grad.argtypes = [vp, ci] + [vp] * 6 + [cf, vp, vp, cu, vp, ci, ctypes.POINTER(vp),
+                                           ctypes.POINTER(ctypes.c_longlong), ci, vp, vp]
+  lib.nfb_train_value_and_grad.restype = ci
+  lib.nfb_adam_step.argtypes = [vp, vp, vp, vp, ctypes.c_longlong, cf, cf, cf, cf, ctypes.c_longlong, vp]
+  lib.nfb_adam_step.restype = ci
   lib.nfb_set_time_alpha.argtypes = [vp, cf]
   lib.nfb_set_time_alpha.restype = ci
   lib.nfb_warp_forward.restype = ci

@@ -52,9 +52,28 @@ static_assert(kX3SmemBytes <= 232448, "shared memory");
 // costs ~120 cycles of tensor-pipe issue, so it is paid once per 12 MMAs).
 constexpr int kX3Slots = 2;
 constexpr int kX3SlotBytes = 2 * kStageBytes;
+// Ring variants (A/B builds, tools/build_variant.py):
+//   default            one full / one empty barrier per slot, one commit per unit
+//   NFB_X3_EARLY_HI    the W_hi half of a slot has its own barriers and is released (second
+//                      commit) as soon as the x_lo W_hi chain is done: its refill starts half a
+//                      unit earlier - hides more of the ~1,500-cycle latency of a bulk copy
+//   NFB_X3_CPASYNC     the three control warps copy the slot with 16-byte cp.async (LDGSTS)
+//                      instead of one bulk copy (lower latency, no multicast)
+#ifdef NFB_X3_EARLY_HI
+constexpr bool kEarlyHi = true;
+#else
+constexpr bool kEarlyHi = false;
+#endif
+#ifdef NFB_X3_CPASYNC
+constexpr bool kCpAsync = true;
+#else
+constexpr bool kCpAsync = false;
+#endif
 struct X3Bars {
-  uint64_t full[kX3Slots];
+  uint64_t full[kX3Slots];       // default: the whole slot; kEarlyHi: the W_lo half
   uint64_t empty[kX3Slots];
+  uint64_t full_hi[kX3Slots];    // kEarlyHi only
+  uint64_t empty_hi[kX3Slots];
   uint64_t acc_ready[2];
   uint64_t x_free;
   uint64_t x_ready[3];
@@ -240,18 +259,26 @@ __device__ __forceinline__ void x3_piece(const float* v, const float4* __restric
 //   barriers in between, ONE commit "weight slot free" and the optional x_free /
 //   accumulator commits.  Returns the probe bits: 1 = the next unit's weight slot has
 //   landed, 2/4/8 = x_ready[0/1/2].
+template <bool kMulticastRelease>
 __device__ __forceinline__ uint32_t issue_x3_tail(uint32_t d, uint64_t a_hi, uint64_t a_lo, uint64_t b_hi,
                                                   uint64_t b_lo, uint32_t idesc, uint32_t bar_empty,
                                                   uint32_t bar_xfree, uint32_t bar_acc, uint32_t probe_w,
                                                   uint32_t par_w, uint32_t probe_x0, uint32_t probe_x1,
-                                                  uint32_t probe_x2, uint32_t par_x) {
+                                                  uint32_t probe_x2, uint32_t par_x,
+                                                  uint32_t bar_empty_hi = 0, uint32_t probe_w_hi = 0) {
   uint32_t out;
   asm volatile(
       "{\n\t"
-      ".reg .pred pt, pw, px0, px1, px2, pd0, pd1, pd2, pcx, pca;\n\t"
+      ".reg .pred pt, pw, pw2, px0, px1, px2, pd0, pd1, pd2, pcx, pca, pmc, peh, pehm, pe2;\n\t"
       ".reg .b64 l1, l2, l3, h1, h2, h3, bh1, bh2, bh3, bl1, bl2, bl3;\n\t"
       ".reg .b32 t0, t1, t2;\n\t"
       "setp.eq.b32 pt, 0, 0;\n\t"
+      "setp.ne.b32 pmc, %17, 0;\n\t"
+      "setp.ne.b32 pe2, %19, 0;\n\t"
+      "setp.ne.b32 peh, %18, 0;\n\t"
+      "and.pred pehm, peh, pmc;\n\t"
+      "@pmc setp.eq.b32 peh, 1, 0;\n\t"
+      "setp.eq.b32 pw2, 0, 0;\n\t"
       "setp.ne.b32 pd0, %12, 0;\n\t"
       "setp.ne.b32 pd1, %13, 0;\n\t"
       "setp.ne.b32 pd2, %14, 0;\n\t"
@@ -268,17 +295,24 @@ __device__ __forceinline__ uint32_t issue_x3_tail(uint32_t d, uint64_t a_hi, uin
       "tcgen05.mma.cta_group::1.kind::f16 [%1], l1, bh1, %6, pt;\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%1], l2, bh2, %6, pt;\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%1], l3, bh3, %6, pt;\n\t"
+      // kEarlyHi: the W_hi half of the slot is free from here on
+      "@peh tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%18];\n\t"
+      "@pehm tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%18], %16;\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%1], %2, %5, %6, pt;\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%1], h1, bl1, %6, pt;\n\t"
       "mbarrier.test_wait.parity.shared::cta.b64 pw, [%10], %11;\n\t"
+      "@pe2 mbarrier.test_wait.parity.shared::cta.b64 pw2, [%19], %11;\n\t"
       "@pd0 mbarrier.test_wait.parity.shared::cta.b64 px0, [%12], %15;\n\t"
       "@pd1 mbarrier.test_wait.parity.shared::cta.b64 px1, [%13], %15;\n\t"
       "@pd2 mbarrier.test_wait.parity.shared::cta.b64 px2, [%14], %15;\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%1], h2, bl2, %6, pt;\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%1], h3, bl3, %6, pt;\n\t"
-      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%7];\n\t"
+      "@!pmc tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%7];\n\t"
+      // CTA-pair build: the weight slot is shared (multicast copies): release it in both CTAs
+      "@pmc tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%7], %16;\n\t"
       "@pcx tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%8];\n\t"
       "@pca tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%9];\n\t"
+      "and.pred pw, pw, pw2;\n\t"
       "selp.u32 %0, 1, 0, pw;\n\t"
       "selp.u32 t0, 2, 0, px0;\n\t"
       "selp.u32 t1, 4, 0, px1;\n\t"
@@ -290,7 +324,8 @@ __device__ __forceinline__ uint32_t issue_x3_tail(uint32_t d, uint64_t a_hi, uin
       : "=r"(out)
       : "r"(d), "l"(a_hi), "l"(a_lo), "l"(b_hi), "l"(b_lo), "r"(idesc), "r"(bar_empty),
         "r"(bar_xfree), "r"(bar_acc), "r"(probe_w), "r"(par_w), "r"(probe_x0), "r"(probe_x1),
-        "r"(probe_x2), "r"(par_x)
+        "r"(probe_x2), "r"(par_x), "h"((uint16_t)0x3), "r"(kMulticastRelease ? 1u : 0u),
+        "r"(bar_empty_hi), "r"(probe_w_hi)
       : "memory");
   return out;
 }
@@ -306,6 +341,14 @@ struct X3Row {
   bool last;         // last sample of its ray
 };
 
+// kPair: launched as clusters of two CTAs that SHARE the weight stream: rank 0 fetches the W_hi
+// half of every slot, rank 1 the W_lo half, each with a multicast bulk copy into both CTAs' rings.
+// Every SM of the chip streams the same 5.6 MB of weights in near lockstep, which makes the L2
+// slices that hold the current unit the bottleneck (148 readers per line: a 32 KB slot took ~1,500
+// cycles to arrive); sharing halves those reads.  Otherwise the two CTAs are independent (own
+// tiles, own MMAs, own TMEM): the only coupling is that a slot is refilled once BOTH issuers have
+// released it (empty barriers count two multicast commits).
+template <bool kPair>
 __global__ void __launch_bounds__(kX3Threads, 1)
 field_x3_kernel(const __grid_constant__ TcProgram prog, const __grid_constant__ X3Consts cst,
                 const FieldArgs args, const uint8_t* __restrict__ wpack, int num_tiles) {
@@ -325,7 +368,10 @@ field_x3_kernel(const __grid_constant__ TcProgram prog, const __grid_constant__ 
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == kMmaWarp * 32) {
-    for (int i = 0; i < kX3Slots; ++i) { mbar_init(&bars->full[i], 1); mbar_init(&bars->empty[i], 1); }
+    for (int i = 0; i < kX3Slots; ++i) {
+      mbar_init(&bars->full[i], kCpAsync ? 96 : 1); mbar_init(&bars->empty[i], kPair ? 2 : 1);
+      mbar_init(&bars->full_hi[i], 1); mbar_init(&bars->empty_hi[i], kPair ? 2 : 1);
+    }
     mbar_init(&bars->acc_ready[0], 1); mbar_init(&bars->acc_ready[1], 1);
     mbar_init(&bars->x_free, 1);
     for (int k = 0; k < 3; ++k) mbar_init(&bars->x_ready[k], kX3EpiThreads);
@@ -333,8 +379,10 @@ field_x3_kernel(const __grid_constant__ TcProgram prog, const __grid_constant__ 
   }
   if (warp == kMmaWarp) tmem_alloc(&bars->tmem_slot, 256);
   tc_fence_before();
-  __syncthreads();
+  if constexpr (kPair) cluster_sync_all();      // the peer's barriers exist before any multicast lands
+  else __syncthreads();
   tc_fence_after();
+  const uint32_t rank = kPair ? cluster_ctarank() : 0u;
   const uint32_t tmem_base = bars->tmem_slot;
   const bool do_warp = args.use_warp && prog.warp_type != 0;
   int first_step = 0;
@@ -354,35 +402,77 @@ field_x3_kernel(const __grid_constant__ TcProgram prog, const __grid_constant__ 
   const bool fuse = args.ray_out != nullptr && !args.warp_only;
   const int tpr = fuse ? args.samples_per_ray / kTileRows : 1;          // tiles per group
   const int groups = num_tiles / tpr;
-  const int my_groups = (int)blockIdx.x < groups ? (groups - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+  // (a CTA pair runs the same number of units - the count of its even member: the ring couples
+  //  them; the odd member's surplus tile lies beyond the end, is computed on clamped rows and never stored)
+  const int bid_n = kPair ? ((int)blockIdx.x & ~1) : (int)blockIdx.x;
+  const int my_groups = bid_n < groups ? (groups - bid_n + (int)gridDim.x - 1) / (int)gridDim.x : 0;
   const int n_my = my_groups * tpr;
   auto tile_of = [&](int i) { return ((int)blockIdx.x + (i / tpr) * (int)gridDim.x) * tpr + (i % tpr); };
 
-  if (warp == kProdWarp) {
+  if (kCpAsync ? warp >= kProdWarp : warp == kProdWarp) {
     // ===================== weight producer =====================
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kCtlRegs));
     uint32_t it = 0, dead = 0;
-    Tracer tr(args, lane == 0 ? 3 : -1);
+    Tracer tr(args, (lane == 0 && warp == kProdWarp) ? 3 : -1);
     for (int ti = 0; ti < n_my; ++ti) {
       for (int si = first_step; si <= last_step; ++si) {
         const TcStep& st = prog.steps[si];
         const uint32_t bytes = 2u * (uint32_t)st.chunk_n * kRowBytes;   // [W_hi | W_lo] of one unit, contiguous
+        const uint32_t half = bytes >> 1;
         const uint8_t* src = wpack + st.w_off;
         const int n = st.n_chunks * st.nkb;               // [chunk][kb]
         for (int u = 0; u < n; ++u, ++it) {
           const int sg = it & (kX3Slots - 1);
           const uint32_t ph = (it / kX3Slots) & 1;
-          mbar_wait(&bars->empty[sg], ph ^ 1, dead);
-          tr.ev(si, u);
-          if (elect_one()) {
-            mbar_arrive_expect_tx(&bars->full[sg], bytes);
-            bulk_g2s(stages + sg * kX3SlotBytes, src + (size_t)u * bytes, bytes, &bars->full[sg]);
+          uint8_t* dst = stages + sg * kX3SlotBytes;
+          const uint8_t* from = src + (size_t)u * bytes;
+          if constexpr (kCpAsync) {
+            // three warps, 16 bytes per lane and instruction; a thread signals "my part has landed"
+            // (generic-proxy writes -> fence.proxy.async before the MMAs may read them)
+            mbar_wait(&bars->empty[sg], ph ^ 1, dead);
+            if (warp == kProdWarp) tr.ev(si, u);
+            const int t96 = (warp - kProdWarp) * 32 + lane;
+            for (uint32_t o = t96 * 16u; o < bytes; o += 96u * 16u) cp_async16(dst + o, from + o);
+            cp_async_commit();
+            cp_async_wait<0>();
+            fence_proxy_async();
+            mbar_arrive(&bars->full[sg]);
+          } else if constexpr (kEarlyHi) {
+            // the two halves of the slot are released (and therefore refilled) separately
+            mbar_wait(&bars->empty_hi[sg], ph ^ 1, dead);
+            tr.ev(si, 2 * u);
+            if (elect_one()) {
+              mbar_arrive_expect_tx(&bars->full_hi[sg], half);
+              if constexpr (kPair) { if (rank == 0) bulk_g2s_multicast(dst, from, half, &bars->full_hi[sg], (uint16_t)0x3); }
+              else bulk_g2s(dst, from, half, &bars->full_hi[sg]);
+            }
+            __syncwarp();
+            mbar_wait(&bars->empty[sg], ph ^ 1, dead);
+            tr.ev(si, 2 * u + 1);
+            if (elect_one()) {
+              mbar_arrive_expect_tx(&bars->full[sg], half);
+              if constexpr (kPair) { if (rank == 1) bulk_g2s_multicast(dst + half, from + half, half, &bars->full[sg], (uint16_t)0x3); }
+              else bulk_g2s(dst + half, from + half, half, &bars->full[sg]);
+            }
+            __syncwarp();
+          } else {
+            mbar_wait(&bars->empty[sg], ph ^ 1, dead);
+            tr.ev(si, u);
+            if (elect_one()) {
+              mbar_arrive_expect_tx(&bars->full[sg], bytes);
+              if constexpr (kPair) {
+                // rank 0: W_hi, rank 1: W_lo - to both CTAs
+                bulk_g2s_multicast(dst + rank * half, from + rank * half, half, &bars->full[sg], (uint16_t)0x3);
+              } else {
+                bulk_g2s(dst, from, bytes, &bars->full[sg]);
+              }
+            }
+            __syncwarp();
           }
-          __syncwarp();
         }
       }
     }
-    if (lane == 0) tr.finish(args, 3);
+    if (lane == 0 && warp == kProdWarp) tr.finish(args, 3);
   } else if (warp == kMmaWarp) {
     // ===================== MMA issuer =====================
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kCtlRegs));
@@ -392,6 +482,7 @@ field_x3_kernel(const __grid_constant__ TcProgram prog, const __grid_constant__ 
       const uint32_t lo_base = ((smem_u32(xh) & 0x3FFFFu) >> 4) | (1u << 16);
       const uint32_t st_lo = ((smem_u32(stages) & 0x3FFFFu) >> 4) | (1u << 16);
       const uint32_t b_full = smem_u32(&bars->full[0]), b_empty = smem_u32(&bars->empty[0]);
+      const uint32_t b_full_hi = smem_u32(&bars->full_hi[0]), b_empty_hi = smem_u32(&bars->empty_hi[0]);
       const uint32_t b_acc0 = smem_u32(&bars->acc_ready[0]), b_acc1 = smem_u32(&bars->acc_ready[1]);
       const uint32_t b_xfree = smem_u32(&bars->x_free);
       const uint32_t b_x0 = smem_u32(&bars->x_ready[0]), b_x1 = smem_u32(&bars->x_ready[1]);
@@ -414,7 +505,10 @@ field_x3_kernel(const __grid_constant__ TcProgram prog, const __grid_constant__ 
             if ((need & 2) && !(ready & 2)) mbar_wait_issuer(&bars->x_ready[0], xr & 1, dead);
             if ((need & 4) && !(ready & 4)) mbar_wait_issuer(&bars->x_ready[1], xr & 1, dead);
             if ((need & 8) && !(ready & 8)) mbar_wait_issuer(&bars->x_ready[2], xr & 1, dead);
-            if (!(ready & 1)) mbar_wait_issuer(&bars->full[sg], wph, dead);
+            if (!(ready & 1)) {
+              if constexpr (kEarlyHi) mbar_wait_issuer(&bars->full_hi[sg], wph, dead);
+              mbar_wait_issuer(&bars->full[sg], wph, dead);
+            }
           }
           issue_half0(d0, ad0, bd, c0.w, flags & kUAccum);               // x_hi W_hi
           // ---- bookkeeping while those MMAs execute ----
@@ -432,10 +526,11 @@ field_x3_kernel(const __grid_constant__ TcProgram prog, const __grid_constant__ 
           bd = desc_hi | (uint64_t)(st_lo + nsg * (kX3SlotBytes >> 4));
           ad0 = desc_hi | (uint64_t)(lo_base + n0.x);
           // W_lo follows W_hi inside the slot: chunk_n rows x 128 B further (c1.z bits 16..)
-          ready = issue_x3_tail(d_cur, a_hi, a_lo, bd_cur, bd_cur + (uint64_t)(c1.z >> 16), idesc,
+          ready = issue_x3_tail<kPair>(d_cur, a_hi, a_lo, bd_cur, bd_cur + (uint64_t)(c1.z >> 16), idesc,
                                 bar_e, (flags & kUCommitXFree) ? b_xfree : 0u,
                                 (flags & kUCommitAcc0) ? b_acc0 : ((flags & kUCommitAcc1) ? b_acc1 : 0u),
-                                b_full + nsg * 8, nwph, px0, px1, px2, nxr & 1);
+                                b_full + nsg * 8, nwph, px0, px1, px2, nxr & 1,
+                                kEarlyHi ? b_empty_hi + sg * 8 : 0u, kEarlyHi ? b_full_hi + nsg * 8 : 0u);
           if (flags & (kUCommitAcc0 | kUCommitAcc1)) tr.ev(c1.w, (flags & kUCommitAcc0) ? 1 : 2);
           if (flags & kUWaitX0) tr.ev(c1.w, 0);
           sg = nsg; wph = nwph; xr = nxr;
@@ -664,7 +759,8 @@ field_x3_kernel(const __grid_constant__ TcProgram prog, const __grid_constant__ 
               }
               const float Ti = (c_T * Wq) * excl;              // accum_prod (model_utils.py:110-113)
               const float w = al * Ti;
-              if (args.ray_weights) args.ray_weights[row.m] = w;
+              const bool live = tile < num_tiles;              // (a CTA pair's surplus tile computes on clamped rows)
+              if (args.ray_weights && live) args.ray_weights[row.m] = w;
               float C = w;                                     // inclusive cumsum of the weights
 #pragma unroll
               for (int sh = 1; sh < 32; sh <<= 1) {
@@ -700,7 +796,7 @@ field_x3_kernel(const __grid_constant__ TcProgram prog, const __grid_constant__ 
               a_med += scan_s[4] + scan_s[5] + scan_s[6] + scan_s[7];
               a_r += tot[0]; a_g += tot[1]; a_b += tot[2]; a_d += tot[3]; a_w += tot[4]; a_wnl += tot[5];
               c_T = c_T * Wall; c_cw += tot[4];
-              if ((tile % tpr) == tpr - 1 && r == 0) {
+              if ((tile % tpr) == tpr - 1 && r == 0 && live) {
                 float rr = a_r, gg = a_g, bb = a_b;
                 if (args.white_bg) { const float bg = 1.f - a_w; rr = rr + bg; gg = gg + bg; bb = bb + bg; }
                 float* ro = args.ray_out + row.ray * 6;
@@ -718,12 +814,14 @@ field_x3_kernel(const __grid_constant__ TcProgram prog, const __grid_constant__ 
     tr.finish(args, 1 + hs);
     tc_fence_before();
   }
-  __syncthreads();
+  if constexpr (kPair) cluster_sync_all();   // nobody exits while the peer may still multicast into it / signal it
+  else __syncthreads();
   if (warp == kMmaWarp) tmem_dealloc(tmem_base, 256);
 }
 
 inline int create_x3(nfb_handle*) {
-  if (cudaFuncSetAttribute(field_x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kX3SmemBytes) != cudaSuccess)
+  if (cudaFuncSetAttribute(field_x3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kX3SmemBytes) != cudaSuccess ||
+      cudaFuncSetAttribute(field_x3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kX3SmemBytes) != cudaSuccess)
     return fail("cannot reserve %d bytes of shared memory for the fp16x3 kernel", kX3SmemBytes);
   return 0;
 }
@@ -735,8 +833,37 @@ inline int run_field_x3(nfb_handle* h, int level, const FieldArgs& a, cudaStream
   if (fuse && (a.samples_per_ray % kTileRows != 0 || a.num_rows % a.samples_per_ray != 0))
     return fail("fused composite needs samples_per_ray to be a multiple of %d", kTileRows);
   const long long groups = fuse ? a.num_rows / a.samples_per_ray : tiles;
+  if (!kCpAsync && groups >= (long long)h->sm_count && h->x3_pair_ok != 0) {
+    // CTA pairs sharing the weight stream (see the kernel): worth it once every SM has work
+    cudaLaunchConfig_t cfg = {};
+    cfg.blockDim = dim3(kX3Threads); cfg.dynamicSmemBytes = kX3SmemBytes; cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    if (h->x3_pair_ok < 0) {
+      // persistent kernel: no more clusters than can be co-resident
+      cfg.gridDim = dim3((unsigned)(h->sm_count & ~1));
+      int n = 0;
+      if (cudaOccupancyMaxActiveClusters(&n, field_x3_kernel<true>, &cfg) != cudaSuccess || n < 1) {
+        cudaGetLastError();
+        h->x3_pair_ok = 0;
+      } else {
+        h->x3_pair_ok = n;
+      }
+    }
+    if (h->x3_pair_ok > 0) {
+      const int grid2 = 2 * (int)std::min<long long>((groups + 1) / 2, h->x3_pair_ok);
+      cfg.gridDim = dim3((unsigned)grid2);
+      cudaError_t le = cudaLaunchKernelEx(&cfg, field_x3_kernel<true>, h->tcprog[level], h->x3c[level], a,
+                                          (const uint8_t*)h->d_wpack, (int)tiles);
+      if (le != cudaSuccess) return fail("field_x3_kernel (CTA pair) launch failed: %s", cudaGetErrorString(le));
+      h->launches++;
+      return 0;
+    }
+  }
   const int grid = (int)std::min<long long>(groups, h->sm_count);
-  field_x3_kernel<<<grid, kX3Threads, kX3SmemBytes, s>>>(h->tcprog[level], h->x3c[level], a, h->d_wpack, (int)tiles);
+  field_x3_kernel<false><<<grid, kX3Threads, kX3SmemBytes, s>>>(h->tcprog[level], h->x3c[level], a, h->d_wpack, (int)tiles);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail("field_x3_kernel launch failed: %s", cudaGetErrorString(e));
   h->launches++;

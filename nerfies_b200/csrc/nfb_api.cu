@@ -715,6 +715,8 @@ void nfb_destroy(nfb_handle* h) {
                    h->d_lower, h->d_upper, h->d_ulin, h->d_window, h->d_cond, h->d_zc, h->d_zf,
                    h->d_wc, h->d_samples, h->d_out_c, h->d_out_f, h->d_in};
   for (float* p : bufs) if (p) cudaFree(p);
+  float* tbufs[] = {h->d_tape, h->d_gpacked, h->d_gwarp, h->d_gapp, h->d_gcam, h->d_dcond, h->d_tr_out, h->d_tr_w, h->d_loss};
+  for (float* p : tbufs) if (p) cudaFree(p);
   if (h->d_ids) cudaFree(h->d_ids);
   for (int l = 0; l < 2; ++l)
     for (int i = 0; i < 2; ++i) if (h->ev[l][i]) cudaEventDestroy(h->ev[l][i]);
@@ -917,3 +919,5 @@ int nfb_warp_forward(nfb_handle* h, int P, const float* points, const unsigned* 
 }
 
 }  // extern "C"
+
+#include "train_api.cuh"

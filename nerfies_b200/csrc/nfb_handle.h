@@ -91,6 +91,11 @@ struct nfb_handle {
   cudaStream_t last_stream = nullptr;  // stream of the previous call (see enter_stream)
   bool last_stream_valid = false;
   cudaEvent_t ev_order = nullptr;
+  // training tier (train_api.cuh): tape + gradient buffers, allocated on first use
+  float* d_tape = nullptr; long long tape_floats = 0;
+  float *d_gpacked = nullptr, *d_gwarp = nullptr, *d_gapp = nullptr, *d_gcam = nullptr;
+  float *d_dcond = nullptr, *d_tr_out = nullptr, *d_tr_w = nullptr, *d_loss = nullptr;
+  int x3_pair_ok = -1;                // fp16x3 CTA-pair launch: -1 unknown, 0 unavailable, n = co-resident clusters
   int debug_bits = 0;                 // FieldArgs::debug bits set through the test hook (abort-path test)
   long long* trace = nullptr;
   int trace_cap = 0;

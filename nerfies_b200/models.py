@@ -316,6 +316,12 @@ class NerfModel:
       self._handle = _Handle(self.nfb_config(), want, self.device)
     return self._handle
 
+  def invalidate_params(self):
+    """Forces the next call to re-upload the parameters (their storage was rewritten in place
+    by a kernel torch does not see, e.g. nfb_adam_step)."""
+    if self._handle is not None:
+      self._handle.param_key = None
+
   def kernel_launches(self) -> int:
     if self._handle is None:
       return 0

@@ -1,12 +1,19 @@
-# Round evidence set (run on the GPU box): bench line with CPU baseline, ncu launch
-# list, one ncu --set full capture of the fine-level field kernel, block-0 timeline.
+# Round evidence set (run on the GPU box): default bench line (fp16x3 headline + bf16 + eval frame
+# + CPU baseline), the other BASELINE workloads, ncu launch list of one step, ncu --set full
+# captures of the two tensor-core field kernels and of the camera kernel, block-0 timelines.
 set -x
-python bench.py --steps 8 --warmup 3 > gpurun_out/bench_bf16_full.json 2> gpurun_out/bench_bf16_full.err
-tail -c 700 gpurun_out/bench_bf16_full.json
-NFB_DEBUG=1 python bench.py --steps 8 --warmup 3 --no-cpu-baseline 2>/dev/null | python tools/benchline.py > gpurun_out/bench_skeleton_only.txt
-cat gpurun_out/bench_skeleton_only.txt
-ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_bf16.csv python bench.py --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_list.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:field_tc -s 3 -c 1 -f -o gpurun_out/prof_tc8 python bench.py --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_tc.log 2>&1
-tail -2 gpurun_out/ncu_tc.log | cut -c1-200
-STEP_LO=0 STEP_HI=40 timeout 200 python tools/trace_tc.py > gpurun_out/tc_timeline.txt 2>&1
-head -4 gpurun_out/tc_timeline.txt
+R=r02
+python bench.py --steps 10 --warmup 3 > gpurun_out/${R}_bench_default_1gpu.json 2> gpurun_out/${R}_bench_default_1gpu.err
+tail -c 600 gpurun_out/${R}_bench_default_1gpu.json
+for w in quarterhd-train vrig-train fullhd-train; do
+  python bench.py --workload $w --steps 5 --no-cpu-baseline > gpurun_out/${R}_bench_$w.json 2> gpurun_out/${R}_bench_$w.err
+done
+ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${R}_launches_fp16x3_ncu.csv python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-also --no-parity > gpurun_out/ncu_list.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:field_x3 -s 3 -c 1 -f -o gpurun_out/${R}_prof_x3 python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-also --no-parity > gpurun_out/ncu_x3.log 2>&1
+tail -2 gpurun_out/ncu_x3.log | cut -c1-200
+ncu --set full --clock-control none --import-source on -k regex:field_tc -s 3 -c 1 -f -o gpurun_out/${R}_prof_tc python bench.py --precision bf16 --steps 1 --warmup 1 --no-cpu-baseline --no-also --no-parity > gpurun_out/ncu_tc.log 2>&1
+ncu --set full --clock-control none -k regex:camera_rays -s 6 -c 2 -f -o gpurun_out/${R}_prof_camera python tools/bench_camera.py > gpurun_out/ncu_cam.log 2>&1
+python tools/bench_camera.py > gpurun_out/${R}_bench_camera.json 2>/dev/null
+python tools/build_variant.py trace -DNFB_TRACE >/dev/null 2>&1 || true
+PREC=fp16x3 STEP_LO=0 STEP_HI=40 timeout 200 python tools/trace_tc.py > gpurun_out/${R}_x3_timeline.txt 2>&1
+head -24 gpurun_out/${R}_x3_timeline.txt

@@ -280,6 +280,15 @@ int nfb_selftest_microbench(int mode, int n, int reps, int nwarps, long long* ou
 int nfb_selftest_gemm2(int K, int N, const float* A, const float* W, float* C, int reps,
                        long long* out, void* stream);
 
+/* A-operand-in-TMEM form of tcgen05.mma, as the fp16x3 field kernel uses it:
+ * C (128 x N) = A (128 x K) W (K x N) as three fp16 chains (A_hi W_hi + A_lo W_hi +
+ * A_hi W_lo, fp32 accumulate), both fp16 images of A written to tensor memory with
+ * tcgen05.st, W from shared memory.  K <= 256, N <= 256; `reps` repeats the chains
+ * (the result is divided by reps).  out (host, 2 x int64, nullable): cycles from the
+ * first issue to completion, number of MMAs.  Hardware self-test; no reference analogue. */
+int nfb_selftest_gemm3(int K, int N, const float* A, const float* W, float* C, int reps,
+                       long long* out, void* stream);
+
 /* Number of CUDA kernels this handle has launched so far (bench accounting). */
 long long nfb_kernel_launches(const nfb_handle* h);
 /* Thread-local description of the last error returned on this thread. */

@@ -17,7 +17,7 @@ SYMBOLS = [
     'nfb_render_samples', 'nfb_sample_pdf', 'nfb_coarse_z_vals',
     'nfb_warp_forward', 'nfb_kernel_launches', 'nfb_last_error', 'nfb_version',
     'nfb_set_profiling', 'nfb_field_time_ms', 'nfb_selftest_gemm', 'nfb_set_trace', 'nfb_selftest_microbench',
-    'nfb_camera_rays', 'nfb_pixels_to_rays', 'nfb_selftest_gemm2',
+    'nfb_camera_rays', 'nfb_pixels_to_rays', 'nfb_selftest_gemm2', 'nfb_selftest_gemm3',
     'nfb_debug_provoke_timeout', 'nfb_set_time_alpha', 'nfb_train_value_and_grad', 'nfb_adam_step',
 ]
 
@@ -165,6 +165,8 @@ def load():
   lib.nfb_pixels_to_rays.restype = ci
   lib.nfb_selftest_gemm2.argtypes = [ci, ci, vp, vp, vp, ci, vp, vp]
   lib.nfb_selftest_gemm2.restype = ci
+  lib.nfb_selftest_gemm3.argtypes = [ci, ci, vp, vp, vp, ci, vp, vp]
+  lib.nfb_selftest_gemm3.restype = ci
   lib.nfb_debug_provoke_timeout.argtypes = [vp, ci]
   lib.nfb_debug_provoke_timeout.restype = ci
   lib.nfb_last_error.argtypes = []

@@ -942,6 +942,13 @@ inline int build_tc_program(nfb_handle* h, int level, long long* wbytes, long lo
         const int a0 = (b < kSrcIn) ? b * kABlockBytes : kXBytes;
         const int a1 = (b < kSrcIn) ? (4 + b) * kABlockBytes : kXBytes + kABlockBytes;
         u.a0_lo = (uint32_t)(a0 >> 4); u.a1_lo = (uint32_t)(a1 >> 4);
+        if (x3) {
+          // fp16x3 (field_tc3.cuh): the activations are in tensor memory - bit 31 + column offset of the
+          // hi / lo image (32 columns per 64-wide K-block); the input block images are in shared memory
+          // at byte offsets 0 / 16 KB.
+          if (b < kSrcIn) { u.a0_lo = 0x80000000u | (uint32_t)(256 + b * 32); u.a1_lo = 0x80000000u | (uint32_t)(384 + b * 32); }
+          else { u.a0_lo = 0u; u.a1_lo = (uint32_t)(kABlockBytes >> 4); }
+        }
         u.dcol = (uint32_t)(c * t.chunk_n); u.idesc = x3 ? make_idesc_f16(kTileRows, t.chunk_n) : make_idesc_bf16(kTileRows, t.chunk_n);
         u.step = (uint32_t)si;
         if (kb) u.flags |= kUAccum;

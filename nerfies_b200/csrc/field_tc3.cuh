@@ -12,17 +12,27 @@
 // kind::tf32 x 3 costs twice the tensor time and 4-byte operands.)  The reference
 // evaluates these layers in fp32 (modules.py:39-62, 107-169).
 //
-// Layout: ONE 128-row tile per CTA at a time (hi and lo images of the activations
-// double the shared-memory footprint, so there is no room for the two sub-tiles of
-// the bf16 kernel): activations hi [4][16 KB] | lo [4][16 KB] | input block hi | lo |
-// weight ring 4 x 16 KB.  The 3x tensor work per layer hides the epilogue without a
-// second tile: chunk 0's epilogue overlaps chunk 1's MMAs, chunk 1's epilogue
-// overlaps the first K-blocks of the next layer (those blocks come from chunk 0).
+// Layout: ONE 128-row tile per CTA at a time.  The ACTIVATIONS LIVE IN TENSOR MEMORY:
+// tcgen05.mma takes its A operand from TMEM ([d], [a], b-desc form), so the epilogue
+// writes the fp16 hi / lo images of a layer's output with tcgen05.st (thread r = TMEM
+// lane r = row r; one 32-bit column holds K elements 2c, 2c+1) and they never touch
+// shared memory:
+//   TMEM (512 columns): accumulators 0..255 (chunk 0 | chunk 1) | A_hi 256..383 | A_lo 384..511
+//   shared memory     : input block hi | lo (2 x 16 KB, the encoded points / conditions,
+//                       SS-form MMAs) | weight ring 6 x 32 KB | scratch | barriers
+// (The first version kept both images in shared memory - 128 KB - which left room for a
+// 2-slot weight ring only: every 256-wide layer stalled ~4 times on the ~1,500-cycle
+// latency of a bulk copy, 10.2 K cycles per layer against 6.1 K of MMA work; it also
+// put the A reads and the epilogue's swizzled stores on the shared-memory port the
+// weights come through.)
+// The 3x tensor work per layer hides the epilogue without a second tile: chunk 0's
+// epilogue overlaps chunk 1's MMAs, chunk 1's epilogue overlaps the first K-blocks of
+// the next layer (those blocks come from chunk 0).
 // Warp roles (384 threads): warps 0-7 epilogue, TWO threads per row (warps w and
 // w + 4 share a TMEM lane quarter and split a chunk's columns), warp 8 issues the
 // MMAs, warp 9 streams the weights (cp.async.bulk, [W_hi | W_lo] per K-block and
 // chunk), warps 10-11 complete the control warpgroup (setmaxnreg 40 / 232).
-// One issuer "unit" = one K-block of one chunk = 12 MMAs (two ring stages).
+// One issuer "unit" = one K-block of one chunk = 12 MMAs = one ring slot.
 #pragma once
 #include <cuda_fp16.h>
 
@@ -35,51 +45,35 @@ using namespace nfb::tc;
 
 constexpr int kX3Threads = 384;
 constexpr int kX3EpiThreads = 256;
-constexpr int kX3Stages = 4;
-constexpr int kXlOff = 4 * kABlockBytes;                 // lo image of the activations
-constexpr int kInhOff = 8 * kABlockBytes;                // == tc::kXBytes: the unit table's input-block offset
-constexpr int kInlOff = 9 * kABlockBytes;
-constexpr int kStageOff = 10 * kABlockBytes;
-constexpr int kPartOff = kStageOff + kX3Stages * kStageBytes;   // alpha partial of the row's second thread
-constexpr int kScanOff = kPartOff + 512;                        // fused composite: cross-warp partials (40 floats)
+// The weight ring: a slot holds [W_hi | W_lo] of one unit (one bulk copy, one "full"
+// barrier, ONE tcgen05.commit to release it: a commit costs ~120 cycles of tensor-pipe
+// issue, so it is paid once per 12 MMAs).
+constexpr int kX3Slots = 6;
+constexpr int kX3SlotBytes = 2 * kStageBytes;                  // 32 KB
+constexpr int kInhOff = 0;                                     // input block, hi image
+constexpr int kInlOff = kABlockBytes;                          // input block, lo image
+constexpr int kStageOff = 2 * kABlockBytes;
+constexpr int kPartOff = kStageOff + kX3Slots * kX3SlotBytes;  // alpha partial of the row's second thread
+constexpr int kScanOff = kPartOff + 512;                       // fused composite: cross-warp partials (40 floats)
 constexpr int kBarOff = kScanOff + 256;
-constexpr int kX3SmemBytes = kBarOff + 128;
-static_assert(kInhOff == kXBytes, "unit table offsets");
+constexpr int kX3SmemBytes = kBarOff + 256;
 static_assert(kX3SmemBytes <= 232448, "shared memory");
+// TMEM columns
+constexpr uint32_t kTmCols = 512, kTmAHi = 256, kTmALo = 384;
+// Unit table (TcUnit::a0_lo / a1_lo, built by build_tc_program): bit 31 set = the A
+// K-block is in TMEM and bits 0..15 are its column offset; otherwise the value is the
+// shared-memory byte offset >> 4 of the input block image.
+constexpr uint32_t kUnitATmem = 0x80000000u;
 
-// The weight ring is two slots of 32 KB; a slot holds [W_hi | W_lo] of one unit
-// (one bulk copy, one "full" barrier, ONE tcgen05.commit to release it: a commit
-// costs ~120 cycles of tensor-pipe issue, so it is paid once per 12 MMAs).
-constexpr int kX3Slots = 2;
-constexpr int kX3SlotBytes = 2 * kStageBytes;
-// Ring variants (A/B builds, tools/build_variant.py):
-//   default            one full / one empty barrier per slot, one commit per unit
-//   NFB_X3_EARLY_HI    the W_hi half of a slot has its own barriers and is released (second
-//                      commit) as soon as the x_lo W_hi chain is done: its refill starts half a
-//                      unit earlier - hides more of the ~1,500-cycle latency of a bulk copy
-//   NFB_X3_CPASYNC     the three control warps copy the slot with 16-byte cp.async (LDGSTS)
-//                      instead of one bulk copy (lower latency, no multicast)
-#ifdef NFB_X3_EARLY_HI
-constexpr bool kEarlyHi = true;
-#else
-constexpr bool kEarlyHi = false;
-#endif
-#ifdef NFB_X3_CPASYNC
-constexpr bool kCpAsync = true;
-#else
-constexpr bool kCpAsync = false;
-#endif
 struct X3Bars {
-  uint64_t full[kX3Slots];       // default: the whole slot; kEarlyHi: the W_lo half
+  uint64_t full[kX3Slots];
   uint64_t empty[kX3Slots];
-  uint64_t full_hi[kX3Slots];    // kEarlyHi only
-  uint64_t empty_hi[kX3Slots];
   uint64_t acc_ready[2];
   uint64_t x_free;
   uint64_t x_ready[3];
   uint32_t tmem_slot;
 };
-static_assert(sizeof(X3Bars) <= 128, "barrier block");
+static_assert(sizeof(X3Bars) <= 256, "barrier block");
 
 // (a, b) -> packed fp16 pairs hi = rn(a, b) and lo = rn(a - hi_a, b - hi_b); `a` is
 // the lower half (the lower K column).  Saturating: |v| > 65504 does not become inf.
@@ -254,80 +248,137 @@ __device__ __forceinline__ void x3_piece(const float* v, const float4* __restric
   }
 }
 
+// First chain of a unit: fence + 4 x (x_hi W_hi).  kTs: A from tensor memory (a = TMEM
+// address, K steps of 8 columns) or from shared memory (a = descriptor, K steps of 32 bytes).
+template <bool kTs>
+__device__ __forceinline__ void issue_x3_head(uint32_t d, uint64_t a_hi, uint64_t b_hi, uint32_t idesc,
+                                              uint32_t accumulate) {
+  if constexpr (kTs) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred pacc, pt;\n\t"
+        ".reg .b32 a1, a2, a3;\n\t"
+        ".reg .b64 b1, b2, b3;\n\t"
+        "tcgen05.fence::after_thread_sync;\n\t"
+        "setp.ne.b32 pacc, %4, 0;\n\t"
+        "setp.eq.b32 pt, 0, 0;\n\t"
+        "add.u32 a1, %1, 8;\n\t add.u32 a2, %1, 16;\n\t add.u32 a3, %1, 24;\n\t"
+        "add.u64 b1, %2, 2;\n\t add.u64 b2, %2, 4;\n\t add.u64 b3, %2, 6;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, pacc;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [a1], b1, %3, pt;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [a2], b2, %3, pt;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [a3], b3, %3, pt;\n\t"
+        "}"
+        ::"r"(d), "r"((uint32_t)a_hi), "l"(b_hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+  } else {
+    issue_half0(d, a_hi, b_hi, idesc, accumulate);
+  }
+}
+
 // Second and third MMA chains of a unit plus everything that follows them:
 //   4 x (x_lo W_hi), 4 x (x_hi W_lo) with the look-ahead probes of the next unit's
 //   barriers in between, ONE commit "weight slot free" and the optional x_free /
 //   accumulator commits.  Returns the probe bits: 1 = the next unit's weight slot has
 //   landed, 2/4/8 = x_ready[0/1/2].
-template <bool kMulticastRelease>
+#define NFB_X3_TAIL_PROLOGUE \
+      ".reg .pred pt, pw, px0, px1, px2, pd0, pd1, pd2, pcx, pca, pmc;\n\t" \
+      ".reg .b32 t0, t1, t2;\n\t" \
+      "setp.eq.b32 pt, 0, 0;\n\t" \
+      "setp.ne.b32 pmc, %17, 0;\n\t" \
+      "setp.ne.b32 pd0, %12, 0;\n\t" \
+      "setp.ne.b32 pd1, %13, 0;\n\t" \
+      "setp.ne.b32 pd2, %14, 0;\n\t" \
+      "setp.ne.b32 pcx, %8, 0;\n\t" \
+      "setp.ne.b32 pca, %9, 0;\n\t" \
+      "setp.eq.b32 px0, 1, 0;\n\t" \
+      "setp.eq.b32 px1, 1, 0;\n\t" \
+      "setp.eq.b32 px2, 1, 0;\n\t" \
+      "add.u64 bh1, %4, 2;\n\t add.u64 bh2, %4, 4;\n\t add.u64 bh3, %4, 6;\n\t" \
+      "add.u64 bl1, %5, 2;\n\t add.u64 bl2, %5, 4;\n\t add.u64 bl3, %5, 6;\n\t"
+#define NFB_X3_TAIL_PROBES \
+      "mbarrier.test_wait.parity.shared::cta.b64 pw, [%10], %11;\n\t" \
+      "@pd0 mbarrier.test_wait.parity.shared::cta.b64 px0, [%12], %15;\n\t" \
+      "@pd1 mbarrier.test_wait.parity.shared::cta.b64 px1, [%13], %15;\n\t" \
+      "@pd2 mbarrier.test_wait.parity.shared::cta.b64 px2, [%14], %15;\n\t"
+#define NFB_X3_TAIL_EPILOGUE \
+      "@!pmc tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%7];\n\t" \
+      /* CTA-pair build: the weight slot is shared (multicast copies): release it in both CTAs */ \
+      "@pmc tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%7], %16;\n\t" \
+      "@pcx tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%8];\n\t" \
+      "@pca tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%9];\n\t" \
+      "selp.u32 %0, 1, 0, pw;\n\t" \
+      "selp.u32 t0, 2, 0, px0;\n\t" \
+      "selp.u32 t1, 4, 0, px1;\n\t" \
+      "selp.u32 t2, 8, 0, px2;\n\t" \
+      "or.b32 %0, %0, t0;\n\t" \
+      "or.b32 %0, %0, t1;\n\t" \
+      "or.b32 %0, %0, t2;\n\t"
+template <bool kMulticastRelease, bool kTs>
 __device__ __forceinline__ uint32_t issue_x3_tail(uint32_t d, uint64_t a_hi, uint64_t a_lo, uint64_t b_hi,
                                                   uint64_t b_lo, uint32_t idesc, uint32_t bar_empty,
                                                   uint32_t bar_xfree, uint32_t bar_acc, uint32_t probe_w,
                                                   uint32_t par_w, uint32_t probe_x0, uint32_t probe_x1,
-                                                  uint32_t probe_x2, uint32_t par_x,
-                                                  uint32_t bar_empty_hi = 0, uint32_t probe_w_hi = 0) {
+                                                  uint32_t probe_x2, uint32_t par_x) {
   uint32_t out;
-  asm volatile(
-      "{\n\t"
-      ".reg .pred pt, pw, pw2, px0, px1, px2, pd0, pd1, pd2, pcx, pca, pmc, peh, pehm, pe2;\n\t"
-      ".reg .b64 l1, l2, l3, h1, h2, h3, bh1, bh2, bh3, bl1, bl2, bl3;\n\t"
-      ".reg .b32 t0, t1, t2;\n\t"
-      "setp.eq.b32 pt, 0, 0;\n\t"
-      "setp.ne.b32 pmc, %17, 0;\n\t"
-      "setp.ne.b32 pe2, %19, 0;\n\t"
-      "setp.ne.b32 peh, %18, 0;\n\t"
-      "and.pred pehm, peh, pmc;\n\t"
-      "@pmc setp.eq.b32 peh, 1, 0;\n\t"
-      "setp.eq.b32 pw2, 0, 0;\n\t"
-      "setp.ne.b32 pd0, %12, 0;\n\t"
-      "setp.ne.b32 pd1, %13, 0;\n\t"
-      "setp.ne.b32 pd2, %14, 0;\n\t"
-      "setp.ne.b32 pcx, %8, 0;\n\t"
-      "setp.ne.b32 pca, %9, 0;\n\t"
-      "setp.eq.b32 px0, 1, 0;\n\t"
-      "setp.eq.b32 px1, 1, 0;\n\t"
-      "setp.eq.b32 px2, 1, 0;\n\t"
-      "add.u64 l1, %3, 2;\n\t add.u64 l2, %3, 4;\n\t add.u64 l3, %3, 6;\n\t"
-      "add.u64 h1, %2, 2;\n\t add.u64 h2, %2, 4;\n\t add.u64 h3, %2, 6;\n\t"
-      "add.u64 bh1, %4, 2;\n\t add.u64 bh2, %4, 4;\n\t add.u64 bh3, %4, 6;\n\t"
-      "add.u64 bl1, %5, 2;\n\t add.u64 bl2, %5, 4;\n\t add.u64 bl3, %5, 6;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%1], %3, %4, %6, pt;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%1], l1, bh1, %6, pt;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%1], l2, bh2, %6, pt;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%1], l3, bh3, %6, pt;\n\t"
-      // kEarlyHi: the W_hi half of the slot is free from here on
-      "@peh tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%18];\n\t"
-      "@pehm tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%18], %16;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%1], %2, %5, %6, pt;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%1], h1, bl1, %6, pt;\n\t"
-      "mbarrier.test_wait.parity.shared::cta.b64 pw, [%10], %11;\n\t"
-      "@pe2 mbarrier.test_wait.parity.shared::cta.b64 pw2, [%19], %11;\n\t"
-      "@pd0 mbarrier.test_wait.parity.shared::cta.b64 px0, [%12], %15;\n\t"
-      "@pd1 mbarrier.test_wait.parity.shared::cta.b64 px1, [%13], %15;\n\t"
-      "@pd2 mbarrier.test_wait.parity.shared::cta.b64 px2, [%14], %15;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%1], h2, bl2, %6, pt;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%1], h3, bl3, %6, pt;\n\t"
-      "@!pmc tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%7];\n\t"
-      // CTA-pair build: the weight slot is shared (multicast copies): release it in both CTAs
-      "@pmc tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%7], %16;\n\t"
-      "@pcx tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%8];\n\t"
-      "@pca tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%9];\n\t"
-      "and.pred pw, pw, pw2;\n\t"
-      "selp.u32 %0, 1, 0, pw;\n\t"
-      "selp.u32 t0, 2, 0, px0;\n\t"
-      "selp.u32 t1, 4, 0, px1;\n\t"
-      "selp.u32 t2, 8, 0, px2;\n\t"
-      "or.b32 %0, %0, t0;\n\t"
-      "or.b32 %0, %0, t1;\n\t"
-      "or.b32 %0, %0, t2;\n\t"
-      "}"
-      : "=r"(out)
-      : "r"(d), "l"(a_hi), "l"(a_lo), "l"(b_hi), "l"(b_lo), "r"(idesc), "r"(bar_empty),
-        "r"(bar_xfree), "r"(bar_acc), "r"(probe_w), "r"(par_w), "r"(probe_x0), "r"(probe_x1),
-        "r"(probe_x2), "r"(par_x), "h"((uint16_t)0x3), "r"(kMulticastRelease ? 1u : 0u),
-        "r"(bar_empty_hi), "r"(probe_w_hi)
-      : "memory");
+  if constexpr (kTs) {
+    asm volatile(
+        "{\n\t"
+        ".reg .b32 l1, l2, l3, h1, h2, h3;\n\t"
+        ".reg .b64 bh1, bh2, bh3, bl1, bl2, bl3;\n\t"
+        NFB_X3_TAIL_PROLOGUE
+        "add.u32 l1, %3, 8;\n\t add.u32 l2, %3, 16;\n\t add.u32 l3, %3, 24;\n\t"
+        "add.u32 h1, %2, 8;\n\t add.u32 h2, %2, 16;\n\t add.u32 h3, %2, 24;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%1], [%3], %4, %6, pt;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%1], [l1], bh1, %6, pt;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%1], [l2], bh2, %6, pt;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%1], [l3], bh3, %6, pt;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%1], [%2], %5, %6, pt;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%1], [h1], bl1, %6, pt;\n\t"
+        NFB_X3_TAIL_PROBES
+        "tcgen05.mma.cta_group::1.kind::f16 [%1], [h2], bl2, %6, pt;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%1], [h3], bl3, %6, pt;\n\t"
+        NFB_X3_TAIL_EPILOGUE
+        "}"
+        : "=r"(out)
+        : "r"(d), "r"((uint32_t)a_hi), "r"((uint32_t)a_lo), "l"(b_hi), "l"(b_lo), "r"(idesc), "r"(bar_empty),
+          "r"(bar_xfree), "r"(bar_acc), "r"(probe_w), "r"(par_w), "r"(probe_x0), "r"(probe_x1),
+          "r"(probe_x2), "r"(par_x), "h"((uint16_t)0x3), "r"(kMulticastRelease ? 1u : 0u)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t"
+        ".reg .b64 l1, l2, l3, h1, h2, h3, bh1, bh2, bh3, bl1, bl2, bl3;\n\t"
+        NFB_X3_TAIL_PROLOGUE
+        "add.u64 l1, %3, 2;\n\t add.u64 l2, %3, 4;\n\t add.u64 l3, %3, 6;\n\t"
+        "add.u64 h1, %2, 2;\n\t add.u64 h2, %2, 4;\n\t add.u64 h3, %2, 6;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%1], %3, %4, %6, pt;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%1], l1, bh1, %6, pt;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%1], l2, bh2, %6, pt;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%1], l3, bh3, %6, pt;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%1], %2, %5, %6, pt;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%1], h1, bl1, %6, pt;\n\t"
+        NFB_X3_TAIL_PROBES
+        "tcgen05.mma.cta_group::1.kind::f16 [%1], h2, bl2, %6, pt;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%1], h3, bl3, %6, pt;\n\t"
+        NFB_X3_TAIL_EPILOGUE
+        "}"
+        : "=r"(out)
+        : "r"(d), "l"(a_hi), "l"(a_lo), "l"(b_hi), "l"(b_lo), "r"(idesc), "r"(bar_empty),
+          "r"(bar_xfree), "r"(bar_acc), "r"(probe_w), "r"(par_w), "r"(probe_x0), "r"(probe_x1),
+          "r"(probe_x2), "r"(par_x), "h"((uint16_t)0x3), "r"(kMulticastRelease ? 1u : 0u)
+        : "memory");
+  }
   return out;
+}
+#undef NFB_X3_TAIL_PROLOGUE
+#undef NFB_X3_TAIL_PROBES
+#undef NFB_X3_TAIL_EPILOGUE
+
+// One 32-column piece of a layer's output (16 packed pairs per image) -> this thread's TMEM lane.
+__device__ __forceinline__ void tst_piece(uint32_t t_lane, int col, const uint32_t* hi16, const uint32_t* lo16) {
+  tmem_st16(t_lane + kTmAHi + (uint32_t)(col >> 1), hi16);
+  tmem_st16(t_lane + kTmALo + (uint32_t)(col >> 1), lo16);
 }
 
 // Row state owned by the two epilogue threads of a row for the lifetime of a tile.
@@ -359,7 +410,6 @@ field_x3_kernel(const __grid_constant__ TcProgram prog, const __grid_constant__ 
     if (threadIdx.x == 0) printf("nfb: dynamic shared memory is not 1024-byte aligned\n");
     __trap();
   }
-  uint8_t* xh = base;                          // [4][16 KB] activations, hi
   uint8_t* inh = base + kInhOff;               // input block, hi
   uint8_t* inl = base + kInlOff;
   uint8_t* stages = base + kStageOff;
@@ -369,15 +419,14 @@ field_x3_kernel(const __grid_constant__ TcProgram prog, const __grid_constant__ 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == kMmaWarp * 32) {
     for (int i = 0; i < kX3Slots; ++i) {
-      mbar_init(&bars->full[i], kCpAsync ? 96 : 1); mbar_init(&bars->empty[i], kPair ? 2 : 1);
-      mbar_init(&bars->full_hi[i], 1); mbar_init(&bars->empty_hi[i], kPair ? 2 : 1);
+      mbar_init(&bars->full[i], 1); mbar_init(&bars->empty[i], kPair ? 2 : 1);
     }
     mbar_init(&bars->acc_ready[0], 1); mbar_init(&bars->acc_ready[1], 1);
     mbar_init(&bars->x_free, 1);
     for (int k = 0; k < 3; ++k) mbar_init(&bars->x_ready[k], kX3EpiThreads);
     fence_barrier_init();
   }
-  if (warp == kMmaWarp) tmem_alloc(&bars->tmem_slot, 256);
+  if (warp == kMmaWarp) tmem_alloc(&bars->tmem_slot, kTmCols);
   tc_fence_before();
   if constexpr (kPair) cluster_sync_all();      // the peer's barriers exist before any multicast lands
   else __syncthreads();
@@ -409,11 +458,11 @@ field_x3_kernel(const __grid_constant__ TcProgram prog, const __grid_constant__ 
   const int n_my = my_groups * tpr;
   auto tile_of = [&](int i) { return ((int)blockIdx.x + (i / tpr) * (int)gridDim.x) * tpr + (i % tpr); };
 
-  if (kCpAsync ? warp >= kProdWarp : warp == kProdWarp) {
+  if (warp == kProdWarp) {
     // ===================== weight producer =====================
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kCtlRegs));
-    uint32_t it = 0, dead = 0;
-    Tracer tr(args, (lane == 0 && warp == kProdWarp) ? 3 : -1);
+    uint32_t sg = 0, ph = 0, dead = 0;
+    Tracer tr(args, lane == 0 ? 3 : -1);
     for (int ti = 0; ti < n_my; ++ti) {
       for (int si = first_step; si <= last_step; ++si) {
         const TcStep& st = prog.steps[si];
@@ -421,68 +470,35 @@ field_x3_kernel(const __grid_constant__ TcProgram prog, const __grid_constant__ 
         const uint32_t half = bytes >> 1;
         const uint8_t* src = wpack + st.w_off;
         const int n = st.n_chunks * st.nkb;               // [chunk][kb]
-        for (int u = 0; u < n; ++u, ++it) {
-          const int sg = it & (kX3Slots - 1);
-          const uint32_t ph = (it / kX3Slots) & 1;
+        for (int u = 0; u < n; ++u) {
           uint8_t* dst = stages + sg * kX3SlotBytes;
           const uint8_t* from = src + (size_t)u * bytes;
-          if constexpr (kCpAsync) {
-            // three warps, 16 bytes per lane and instruction; a thread signals "my part has landed"
-            // (generic-proxy writes -> fence.proxy.async before the MMAs may read them)
-            mbar_wait(&bars->empty[sg], ph ^ 1, dead);
-            if (warp == kProdWarp) tr.ev(si, u);
-            const int t96 = (warp - kProdWarp) * 32 + lane;
-            for (uint32_t o = t96 * 16u; o < bytes; o += 96u * 16u) cp_async16(dst + o, from + o);
-            cp_async_commit();
-            cp_async_wait<0>();
-            fence_proxy_async();
-            mbar_arrive(&bars->full[sg]);
-          } else if constexpr (kEarlyHi) {
-            // the two halves of the slot are released (and therefore refilled) separately
-            mbar_wait(&bars->empty_hi[sg], ph ^ 1, dead);
-            tr.ev(si, 2 * u);
-            if (elect_one()) {
-              mbar_arrive_expect_tx(&bars->full_hi[sg], half);
-              if constexpr (kPair) { if (rank == 0) bulk_g2s_multicast(dst, from, half, &bars->full_hi[sg], (uint16_t)0x3); }
-              else bulk_g2s(dst, from, half, &bars->full_hi[sg]);
+          mbar_wait(&bars->empty[sg], ph ^ 1, dead);
+          tr.ev(si, u);
+          if (elect_one()) {
+            mbar_arrive_expect_tx(&bars->full[sg], bytes);
+            if constexpr (kPair) {
+              // rank 0: W_hi, rank 1: W_lo - to both CTAs
+              bulk_g2s_multicast(dst + rank * half, from + rank * half, half, &bars->full[sg], (uint16_t)0x3);
+            } else {
+              bulk_g2s(dst, from, bytes, &bars->full[sg]);
             }
-            __syncwarp();
-            mbar_wait(&bars->empty[sg], ph ^ 1, dead);
-            tr.ev(si, 2 * u + 1);
-            if (elect_one()) {
-              mbar_arrive_expect_tx(&bars->full[sg], half);
-              if constexpr (kPair) { if (rank == 1) bulk_g2s_multicast(dst + half, from + half, half, &bars->full[sg], (uint16_t)0x3); }
-              else bulk_g2s(dst + half, from + half, half, &bars->full[sg]);
-            }
-            __syncwarp();
-          } else {
-            mbar_wait(&bars->empty[sg], ph ^ 1, dead);
-            tr.ev(si, u);
-            if (elect_one()) {
-              mbar_arrive_expect_tx(&bars->full[sg], bytes);
-              if constexpr (kPair) {
-                // rank 0: W_hi, rank 1: W_lo - to both CTAs
-                bulk_g2s_multicast(dst + rank * half, from + rank * half, half, &bars->full[sg], (uint16_t)0x3);
-              } else {
-                bulk_g2s(dst, from, bytes, &bars->full[sg]);
-              }
-            }
-            __syncwarp();
           }
+          __syncwarp();
+          if (++sg == kX3Slots) { sg = 0; ph ^= 1; }
         }
       }
     }
-    if (lane == 0 && warp == kProdWarp) tr.finish(args, 3);
+    if (lane == 0) tr.finish(args, 3);
   } else if (warp == kMmaWarp) {
     // ===================== MMA issuer =====================
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kCtlRegs));
     if (elect_one()) {
       Tracer tr(args, 0);
       const uint64_t desc_hi = make_smem_desc(0) & 0xFFFFFFFF00000000ull;
-      const uint32_t lo_base = ((smem_u32(xh) & 0x3FFFFu) >> 4) | (1u << 16);
+      const uint32_t lo_base = ((smem_u32(base) & 0x3FFFFu) >> 4) | (1u << 16);
       const uint32_t st_lo = ((smem_u32(stages) & 0x3FFFFu) >> 4) | (1u << 16);
       const uint32_t b_full = smem_u32(&bars->full[0]), b_empty = smem_u32(&bars->empty[0]);
-      const uint32_t b_full_hi = smem_u32(&bars->full_hi[0]), b_empty_hi = smem_u32(&bars->empty_hi[0]);
       const uint32_t b_acc0 = smem_u32(&bars->acc_ready[0]), b_acc1 = smem_u32(&bars->acc_ready[1]);
       const uint32_t b_xfree = smem_u32(&bars->x_free);
       const uint32_t b_x0 = smem_u32(&bars->x_ready[0]), b_x1 = smem_u32(&bars->x_ready[1]);
@@ -496,7 +512,11 @@ field_x3_kernel(const __grid_constant__ TcProgram prog, const __grid_constant__ 
       uint4 n0 = utab[2 * un], n1 = utab[2 * un + 1];
       uint32_t d0 = tmem_base + c0.z;
       uint64_t bd = desc_hi | (uint64_t)st_lo;
-      uint64_t ad0 = desc_hi | (uint64_t)(lo_base + c0.x);
+      // A operand of a K-block: TMEM address (activations) or shared-memory descriptor (input block)
+      auto a_op = [&](uint32_t v) -> uint64_t {
+        return (v & kUnitATmem) ? (uint64_t)(tmem_base + (v & 0xffffu)) : (desc_hi | (uint64_t)(lo_base + v));
+      };
+      uint64_t ad0 = a_op(c0.x);
       for (int ti = 0; ti < n_my; ++ti) {
         for (int u = u_begin; u < u_end; ++u) {
           const uint32_t flags = c1.x, need = c1.y;
@@ -505,32 +525,35 @@ field_x3_kernel(const __grid_constant__ TcProgram prog, const __grid_constant__ 
             if ((need & 2) && !(ready & 2)) mbar_wait_issuer(&bars->x_ready[0], xr & 1, dead);
             if ((need & 4) && !(ready & 4)) mbar_wait_issuer(&bars->x_ready[1], xr & 1, dead);
             if ((need & 8) && !(ready & 8)) mbar_wait_issuer(&bars->x_ready[2], xr & 1, dead);
-            if (!(ready & 1)) {
-              if constexpr (kEarlyHi) mbar_wait_issuer(&bars->full_hi[sg], wph, dead);
-              mbar_wait_issuer(&bars->full[sg], wph, dead);
-            }
+            if (!(ready & 1)) mbar_wait_issuer(&bars->full[sg], wph, dead);
           }
-          issue_half0(d0, ad0, bd, c0.w, flags & kUAccum);               // x_hi W_hi
+          const bool ts = (c0.x & kUnitATmem) != 0;
+          if (ts) issue_x3_head<true>(d0, ad0, bd, c0.w, flags & kUAccum);     // x_hi W_hi
+          else issue_x3_head<false>(d0, ad0, bd, c0.w, flags & kUAccum);
           // ---- bookkeeping while those MMAs execute ----
           if (++un >= u_end) un -= n_u;
           const uint4 f0 = utab[2 * un], f1 = utab[2 * un + 1];          // table entry two units ahead
-          const uint32_t nsg = (sg + 1) & (kX3Slots - 1);
+          const uint32_t nsg = sg + 1 == kX3Slots ? 0u : sg + 1;
           const uint32_t nwph = wph ^ (nsg == 0 ? 1u : 0u);
           const uint32_t nxr = xr + ((flags & kUStepEnd) ? 1u : 0u);
-          const uint64_t a_lo = desc_hi | (uint64_t)(lo_base + c0.y);
+          const uint64_t a_lo = a_op(c0.y);
           const uint32_t px0 = (c1.z & 2) ? b_x0 : 0u, px1 = (c1.z & 4) ? b_x1 : 0u;
           const uint32_t px2 = (c1.z & 8) ? b_x2 : 0u;
           const uint32_t d_cur = d0, idesc = c0.w, bar_e = b_empty + sg * 8;
           const uint64_t bd_cur = bd, a_hi = ad0;
           d0 = tmem_base + n0.z;
           bd = desc_hi | (uint64_t)(st_lo + nsg * (kX3SlotBytes >> 4));
-          ad0 = desc_hi | (uint64_t)(lo_base + n0.x);
+          ad0 = a_op(n0.x);
           // W_lo follows W_hi inside the slot: chunk_n rows x 128 B further (c1.z bits 16..)
-          ready = issue_x3_tail<kPair>(d_cur, a_hi, a_lo, bd_cur, bd_cur + (uint64_t)(c1.z >> 16), idesc,
-                                bar_e, (flags & kUCommitXFree) ? b_xfree : 0u,
-                                (flags & kUCommitAcc0) ? b_acc0 : ((flags & kUCommitAcc1) ? b_acc1 : 0u),
-                                b_full + nsg * 8, nwph, px0, px1, px2, nxr & 1,
-                                kEarlyHi ? b_empty_hi + sg * 8 : 0u, kEarlyHi ? b_full_hi + nsg * 8 : 0u);
+          const uint64_t b_lo = bd_cur + (uint64_t)(c1.z >> 16);
+          const uint32_t bar_x = (flags & kUCommitXFree) ? b_xfree : 0u;
+          const uint32_t bar_a = (flags & kUCommitAcc0) ? b_acc0 : ((flags & kUCommitAcc1) ? b_acc1 : 0u);
+          if (ts)
+            ready = issue_x3_tail<kPair, true>(d_cur, a_hi, a_lo, bd_cur, b_lo, idesc, bar_e, bar_x, bar_a,
+                                               b_full + nsg * 8, nwph, px0, px1, px2, nxr & 1);
+          else
+            ready = issue_x3_tail<kPair, false>(d_cur, a_hi, a_lo, bd_cur, b_lo, idesc, bar_e, bar_x, bar_a,
+                                                b_full + nsg * 8, nwph, px0, px1, px2, nxr & 1);
           if (flags & (kUCommitAcc0 | kUCommitAcc1)) tr.ev(c1.w, (flags & kUCommitAcc0) ? 1 : 2);
           if (flags & kUWaitX0) tr.ev(c1.w, 0);
           sg = nsg; wph = nwph; xr = nxr;
@@ -549,7 +572,6 @@ field_x3_kernel(const __grid_constant__ TcProgram prog, const __grid_constant__ 
     const int qd = warp & 3;                           // TMEM lane quarter
     const int r = qd * 32 + lane;                      // row within the tile
     const uint32_t t_lane = tmem_base + (((uint32_t)qd * 32) << 16);
-    const uint32_t xs_a0 = smem_u32(xh) + r * kRowBytes + ((r & 7) << 4);   // see sts_piece()
     const int cb = hs * 4, ce = cb + 4;                // input-block chunks this thread writes
     Tracer tr(args, (lane == 0 && qd == 0) ? 1 + hs : -1);
     uint32_t n_acc0 = 0, n_acc1 = 0, n_free = 0, dead = 0;
@@ -641,17 +663,14 @@ field_x3_kernel(const __grid_constant__ TcProgram prog, const __grid_constant__ 
           tr.ev(si, 1);
           mbar_wait(&bars->x_free, n_free++ & 1, dead);
           tr.ev(si, 2);
-          sts_piece(xs_a0, col0, ph);
-          sts_piece(xs_a0 + kXlOff, col0, pl);
-          if (wide) {
-            sts_piece(xs_a0, col0 + 32, ph + 16);
-            sts_piece(xs_a0 + kXlOff, col0 + 32, pl + 16);
-          }
+          tst_piece(t_lane, col0, ph, pl);
+          if (wide) tst_piece(t_lane, col0 + 32, ph + 16, pl + 16);
           // The input block is the first K-block of the next step (read right after
           // x_ready[0]); every earlier reader of it (the skip layer) is complete.
           if (st.write_cond)
             cond_to_block_x3(inh, inl, r, args.cond + row.ray * prog.cond_stride + prog.G, prog.rc, cb, ce);
-          fence_proxy_async();
+          tmem_st_wait();                               // the TMEM stores have completed ...
+          if (st.write_cond) fence_proxy_async();       // ... and the input-block stores are visible to the MMAs
           tc_fence_before();
           mbar_arrive(&bars->x_ready[0]);
           tr.ev(si, 3);
@@ -666,21 +685,18 @@ field_x3_kernel(const __grid_constant__ TcProgram prog, const __grid_constant__ 
             tmem_ld32(t_lane + col1 + 32, vb);
             tmem_ld_wait();
             x3_piece(va, bias4 + (col1 >> 2), inv_s, relu, adot, cst.alpha4 + (col1 >> 2), row.alpha, ph, pl);
-            sts_piece(xs_a0, col1, ph);
-            sts_piece(xs_a0 + kXlOff, col1, pl);
+            tst_piece(t_lane, col1, ph, pl);
             x3_piece(vb, bias4 + (col1 >> 2) + 8, inv_s, relu, adot, cst.alpha4 + (col1 >> 2) + 8, row.alpha, ph, pl);
-            sts_piece(xs_a0, col1 + 32, ph);
-            sts_piece(xs_a0 + kXlOff, col1 + 32, pl);
+            tst_piece(t_lane, col1 + 32, ph, pl);
           } else {
             float va[32];
             tmem_ld32(t_lane + col1, va);
             tmem_ld_wait();
             x3_piece(va, bias4 + (col1 >> 2), inv_s, relu, adot, cst.alpha4 + (col1 >> 2), row.alpha, ph, pl);
-            sts_piece(xs_a0, col1, ph);
-            sts_piece(xs_a0 + kXlOff, col1, pl);
+            tst_piece(t_lane, col1, ph, pl);
           }
           if (adot && hs == 1) alpha_part[r] = row.alpha;   // read by the row's first thread at the rgb step
-          fence_proxy_async();
+          tmem_st_wait();
           tc_fence_before();
           mbar_arrive(&bars->x_ready[1]);
           mbar_arrive(&bars->x_ready[2]);
@@ -816,7 +832,7 @@ field_x3_kernel(const __grid_constant__ TcProgram prog, const __grid_constant__ 
   }
   if constexpr (kPair) cluster_sync_all();   // nobody exits while the peer may still multicast into it / signal it
   else __syncthreads();
-  if (warp == kMmaWarp) tmem_dealloc(tmem_base, 256);
+  if (warp == kMmaWarp) tmem_dealloc(tmem_base, kTmCols);
 }
 
 inline int create_x3(nfb_handle*) {
@@ -833,7 +849,7 @@ inline int run_field_x3(nfb_handle* h, int level, const FieldArgs& a, cudaStream
   if (fuse && (a.samples_per_ray % kTileRows != 0 || a.num_rows % a.samples_per_ray != 0))
     return fail("fused composite needs samples_per_ray to be a multiple of %d", kTileRows);
   const long long groups = fuse ? a.num_rows / a.samples_per_ray : tiles;
-  if (!kCpAsync && groups >= (long long)h->sm_count && h->x3_pair_ok != 0) {
+  if (groups >= (long long)h->sm_count && h->x3_pair_ok != 0) {
     // CTA pairs sharing the weight stream (see the kernel): worth it once every SM has work
     cudaLaunchConfig_t cfg = {};
     cfg.blockDim = dim3(kX3Threads); cfg.dynamicSmemBytes = kX3SmemBytes; cfg.stream = s;

@@ -19,6 +19,7 @@
 #include "tc_common.cuh"
 #include "tc_selftest.cuh"
 #include "tc_selftest2.cuh"
+#include "tc_selftest3.cuh"
 #ifdef NFB_WITH_TC
 #include "field_tc.cuh"
 #include "field_tc3.cuh"
@@ -626,6 +627,49 @@ int nfb_selftest_gemm2(int K, int N, const float* A, const float* W, float* C, i
   if (e == cudaSuccess) e = cudaMemcpy(h_out, d_out, sizeof(h_out), cudaMemcpyDeviceToHost);
   cudaFree(d_map); cudaFree(d_w); cudaFree(d_out);
   if (e != cudaSuccess) return fail("selftest2 kernel failed: %s", cudaGetErrorString(e));
+  if (out) { out[0] = h_out[0]; out[1] = h_out[1]; }
+  return abort_check();
+}
+
+int nfb_selftest_gemm3(int K, int N, const float* A, const float* W, float* C, int reps, long long* out,
+                       void* stream) {
+  using namespace nfb::tc;
+  if (K < 1 || K > kSelf3MaxKb * kBlockK || N < 1 || N > 256) return fail("selftest3: K<=256, N<=256");
+  if (reps < 1) return fail("selftest3: reps must be >= 1");
+  if ((long long)((K + kBlockK - 1) / kBlockK) * 2 * ((N + 15) / 16 * 16) * kRowBytes > kSelf3WBytes)
+    return fail("selftest3: the packed weights must fit %d bytes of shared memory", kSelf3WBytes);
+  if (ensure_abort_flag() || abort_check()) return -1;
+  cudaStream_t s = (cudaStream_t)stream;
+  const int nkb = (K + kBlockK - 1) / kBlockK;
+  const int n_rows = (N + 15) / 16 * 16;
+  std::vector<int> k_map(nkb * kBlockK, -1);
+  for (int k = 0; k < K; ++k) k_map[k] = k;
+  int* d_map = nullptr;
+  uint8_t* d_w = nullptr;
+  long long* d_out = nullptr;
+  float* d_max = nullptr;
+  NFB_CUDA(cudaMalloc(&d_map, k_map.size() * sizeof(int)));
+  NFB_CUDA(cudaMalloc(&d_w, (size_t)nkb * 2 * n_rows * kRowBytes));
+  NFB_CUDA(cudaMalloc(&d_out, 2 * sizeof(long long)));
+  NFB_CUDA(cudaMalloc(&d_max, sizeof(float)));
+  NFB_CUDA(cudaMemsetAsync(d_out, 0, 2 * sizeof(long long), s));
+  NFB_CUDA(cudaMemsetAsync(d_max, 0, sizeof(float), s));
+  NFB_CUDA(cudaMemcpyAsync(d_map, k_map.data(), k_map.size() * sizeof(int), cudaMemcpyHostToDevice, s));
+  absmax_kernel<<<32, 256, 0, s>>>(W, (long long)K * N, d_max);
+  const long long total = (long long)nkb * n_rows * kBlockK;
+  pack_weight_x3_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(W, N, d_map, nkb, N, n_rows, d_max, d_w);
+  float h_max = 0.f;
+  NFB_CUDA(cudaMemcpyAsync(&h_max, d_max, sizeof(float), cudaMemcpyDeviceToHost, s));
+  NFB_CUDA(cudaStreamSynchronize(s));
+  const float inv_scale = 1.f / x3_weight_scale(h_max) / (float)reps;
+  NFB_CUDA(cudaFuncSetAttribute(tc_selftest3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSelf3SmemBytes));
+  tc_selftest3_kernel<<<1, 160, kSelf3SmemBytes, s>>>(A, K, d_w, nkb, n_rows, N, inv_scale, C, reps, d_out);
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+  long long h_out[2] = {0, 0};
+  if (e == cudaSuccess) e = cudaMemcpy(h_out, d_out, sizeof(h_out), cudaMemcpyDeviceToHost);
+  cudaFree(d_map); cudaFree(d_w); cudaFree(d_out); cudaFree(d_max);
+  if (e != cudaSuccess) return fail("selftest3 kernel failed: %s", cudaGetErrorString(e));
   if (out) { out[0] = h_out[0]; out[1] = h_out[1]; }
   return abort_check();
 }

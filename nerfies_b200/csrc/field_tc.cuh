@@ -806,6 +806,29 @@ inline int tc_fail(const char* what) {
   return fail("the tcgen05 paths (precision bf16 / fp16x3) do not support this model: %s; use precision fp32", what);
 }
 
+// fp16x3 (field_tc3.cuh): issue order of a step's (chunk, K-block) units.  A layer's output
+// reaches the next layer in two instalments: the columns of chunk 0 (activation blocks
+// < split) when the chunk-0 epilogue is done, the rest after the chunk-1 epilogue, which
+// starts only when the layer's last MMA has completed.  "Phase A" K-blocks (the input block
+// and blocks < split of the previous step) are therefore issued for BOTH chunks first, then
+// the "phase B" K-blocks: the MMAs that overlap the previous chunk-1 epilogue are n_chunks x
+// |A| units instead of |A|, and the chunk-0 accumulator completes two units before the end of
+// the step so that its epilogue overlaps the tail.  Returns the number of units.
+inline int x3_unit_order(const TcProgram& tp, int si, int* oc, int* okb) {
+  const TcStep& t = tp.steps[si];
+  const bool after_heads = si > 0 && tp.steps[si - 1].epi != kEpiHidden;
+  int split = 99;
+  if (si > 0 && !after_heads && tp.steps[si - 1].n_chunks == 2) split = tp.steps[si - 1].chunk_n / kBlockK;
+  int n = 0;
+  for (int phase = 0; phase < 2; ++phase)
+    for (int c = 0; c < t.n_chunks; ++c)
+      for (int kb = 0; kb < t.nkb; ++kb) {
+        const bool late = t.src[kb] < kSrcIn && t.src[kb] >= split;
+        if ((int)late == phase) { oc[n] = c; okb[n] = kb; ++n; }
+      }
+  return n;
+}
+
 inline int build_tc_program(nfb_handle* h, int level, long long* wbytes, long long* aux_floats) {
   const FieldProgram& fp = h->prog[level];
   TcProgram& tp = h->tcprog[level];
@@ -922,6 +945,55 @@ inline int build_tc_program(nfb_handle* h, int level, long long* wbytes, long lo
   for (int si = 0; si < tp.n_steps; ++si) {
     const TcStep& t = tp.steps[si];
     tp.unit_begin[si] = tp.n_units;
+    if (x3) {
+      // ---- fp16x3: phase-ordered units (x3_unit_order) ----
+      int oc[16], okb[16];
+      const int n = x3_unit_order(tp, si, oc, okb);
+      const bool after_heads = si > 0 && tp.steps[si - 1].epi != kEpiHidden;
+      const int split = (si > 0 && !after_heads && tp.steps[si - 1].n_chunks == 2) ? tp.steps[si - 1].chunk_n / kBlockK : 99;
+      if (tp.n_units + n > kMaxTcUnits) return tc_fail("too many weight units");
+      const int first = tp.n_units;
+      int last_of_chunk[2] = {-1, -1}, first_of_chunk[2] = {-1, -1}, first_late = -1, last_low = -1;
+      for (int i = 0; i < n; ++i) {
+        const int c = oc[i], kb = okb[i], b = t.src[kb];
+        if (first_of_chunk[c] < 0) first_of_chunk[c] = i;
+        last_of_chunk[c] = i;
+        if (b < kSrcIn && b >= split && first_late < 0) first_late = i;
+        // readers of the activation blocks this step's chunk-0 epilogue overwrites
+        if (t.n_chunks == 2 && b < kSrcIn && b < t.chunk_n / kBlockK) last_low = i;
+      }
+      for (int i = 0; i < n; ++i) {
+        TcUnit& u = tp.units[tp.n_units++];
+        memset(&u, 0, sizeof(u));
+        const int c = oc[i], kb = okb[i], b = t.src[kb];
+        // the activations are in tensor memory - bit 31 + column offset of the hi / lo image (32 columns per
+        // 64-wide K-block); the input block images are in shared memory at byte offsets 0 / 16 KB
+        if (b < kSrcIn) { u.a0_lo = 0x80000000u | (uint32_t)(256 + b * 32); u.a1_lo = 0x80000000u | (uint32_t)(384 + b * 32); }
+        else { u.a0_lo = 0u; u.a1_lo = (uint32_t)(kABlockBytes >> 4); }
+        u.dcol = (uint32_t)(c * t.chunk_n); u.idesc = make_idesc_f16(kTileRows, t.chunk_n);
+        u.step = (uint32_t)si;
+        if (i != first_of_chunk[c]) u.flags |= kUAccum;
+        if (i == last_of_chunk[c]) u.flags |= (c == 0 ? kUCommitAcc0 : kUCommitAcc1);
+        // x_ready[1] = "the previous chunk-1 epilogue has read its accumulator" (the first MMA of this step's
+        // chunk 1 overwrites it), x_ready[2] = "... has stored its outputs" (the phase-B K-blocks)
+        if (t.n_chunks == 2 && i == first_of_chunk[1]) u.flags |= kUWaitX1;
+        if (i == first_late) u.flags |= kUWaitX2;
+        if (t.n_chunks == 2 && i == (last_low >= 0 ? last_low : 0)) u.flags |= kUCommitXFree;
+      }
+      tp.units[first].flags |= kUWaitX0;
+      TcUnit& last = tp.units[tp.n_units - 1];
+      if (t.n_chunks != 2) last.flags |= kUWaitX1;     // every phase is consumed before the final commit
+      if (first_late < 0) last.flags |= kUWaitX2;
+      last.flags |= kUStepEnd;
+      // issue-order position of every (chunk, K-block): the weight units are packed in that order
+      for (auto& job : h->tc_jobs)
+        if (job.level == level && job.step == si) {
+          job.unit_pos.assign((size_t)t.nkb, 0);
+          for (int i = 0; i < n; ++i)
+            if (oc[i] == job.chunk) job.unit_pos[(size_t)okb[i]] = i;
+        }
+      continue;
+    }
     // A step that can start a tile pair (step 0, or the first NeRF step when the
     // warp is skipped) follows a 1-chunk step or the prologue: nothing to split.
     const bool after_heads = si > 0 && tp.steps[si - 1].epi != kEpiHidden;
@@ -942,14 +1014,7 @@ inline int build_tc_program(nfb_handle* h, int level, long long* wbytes, long lo
         const int a0 = (b < kSrcIn) ? b * kABlockBytes : kXBytes;
         const int a1 = (b < kSrcIn) ? (4 + b) * kABlockBytes : kXBytes + kABlockBytes;
         u.a0_lo = (uint32_t)(a0 >> 4); u.a1_lo = (uint32_t)(a1 >> 4);
-        if (x3) {
-          // fp16x3 (field_tc3.cuh): the activations are in tensor memory - bit 31 + column offset of the
-          // hi / lo image (32 columns per 64-wide K-block); the input block images are in shared memory
-          // at byte offsets 0 / 16 KB.
-          if (b < kSrcIn) { u.a0_lo = 0x80000000u | (uint32_t)(256 + b * 32); u.a1_lo = 0x80000000u | (uint32_t)(384 + b * 32); }
-          else { u.a0_lo = 0u; u.a1_lo = (uint32_t)(kABlockBytes >> 4); }
-        }
-        u.dcol = (uint32_t)(c * t.chunk_n); u.idesc = x3 ? make_idesc_f16(kTileRows, t.chunk_n) : make_idesc_bf16(kTileRows, t.chunk_n);
+        u.dcol = (uint32_t)(c * t.chunk_n); u.idesc = make_idesc_bf16(kTileRows, t.chunk_n);
         u.step = (uint32_t)si;
         if (kb) u.flags |= kUAccum;
         if (!have1 && (c == 1 || kb >= kb_need)) { u.flags |= kUWaitX1; have1 = true; }
@@ -1051,11 +1116,17 @@ inline int pack_tc(nfb_handle* h, cudaStream_t s) {
     const long long total = (long long)t.nkb * t.chunk_n * kBlockK;
     uint8_t* dst = h->d_wpack + t.w_off + (size_t)(x3 ? 2 : 1) * j.chunk * t.nkb * t.chunk_n * kRowBytes;
     // source columns n0.. of the fp32 (K x npad) matrix: shift the base pointer.
-    if (x3)
-      pack_weight_x3_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(
-          h->d_packed + j.simt_w_off + j.n0, j.ld, d_maps + map_off, t.nkb, j.n - j.n0, t.chunk_n,
-          h->d_aux + h->tcprog[j.level].scale_off + j.step, dst);
-    else
+    if (x3) {
+      // one launch per K-block: its unit [W_hi | W_lo] goes to its issue-order position in the step
+      const long long per = (long long)t.chunk_n * kBlockK;
+      for (int kb = 0; kb < t.nkb; ++kb) {
+        uint8_t* udst = h->d_wpack + t.w_off + (size_t)j.unit_pos[(size_t)kb] * 2 * t.chunk_n * kRowBytes;
+        pack_weight_x3_kernel<<<(unsigned)((per + 255) / 256), 256, 0, s>>>(
+            h->d_packed + j.simt_w_off + j.n0, j.ld, d_maps + map_off + (size_t)kb * kBlockK, 1, j.n - j.n0, t.chunk_n,
+            h->d_aux + h->tcprog[j.level].scale_off + j.step, udst);
+        if (kb) h->launches++;
+      }
+    } else
     pack_weight_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(
         h->d_packed + j.simt_w_off + j.n0, j.ld, d_maps + map_off, t.nkb, j.n - j.n0, t.chunk_n,
         reinterpret_cast<__nv_bfloat16*>(dst));

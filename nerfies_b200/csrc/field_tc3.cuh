@@ -70,7 +70,7 @@ struct X3Bars {
   uint64_t empty[kX3Slots];
   uint64_t acc_ready[2];
   uint64_t x_free;
-  uint64_t x_ready[3];
+  uint64_t x_ready[3];           // [0] chunk-0 epilogue done | [1] chunk-1 accumulator read | [2] chunk-1 epilogue done
   uint32_t tmem_slot;
 };
 static_assert(sizeof(X3Bars) <= 256, "barrier block");
@@ -224,13 +224,51 @@ __device__ __forceinline__ void cond_to_block_x3(uint8_t* bh, uint8_t* bl, int r
 // dot product in fp32), split into fp16 hi / lo pairs.
 // `inv_s` undoes the power-of-two weight scale of the layer (x3_weight_scale): acc * inv_s is
 // exact, so fma(acc, inv_s, bias) rounds exactly like the unscaled acc + bias.
-__device__ __forceinline__ void x3_piece(const float* v, const float4* __restrict__ bq4, float inv_s, bool relu,
-                                         bool adot, const float4* __restrict__ aw4, float& alpha,
-                                         uint32_t* hi16, uint32_t* lo16) {
+//
+// The split.  hi = v with the fp32 mantissa truncated to fp16's 11 significant bits (one
+// LOP3; the conversion to fp16 is then exact), lo = fp16(v - hi) (the subtraction is exact;
+// lo carries the next 11 of the remaining 13 bits): v - (hi + lo) <= 2^-23 |v|, the same
+// bound as a round-to-nearest split, for 5 instructions per two elements (2 LOP3, FADD2,
+// 2 F2FP) instead of 8.  ReLU rides on the conversions (cvt.relu): for v < 0 both
+// hi = trunc(v) and v - trunc(v) are <= 0 and convert to +0.  Below fp16's normal range
+// (|v| < 2^-14) the conversion of hi rounds to the subnormal grid and lo does not see that
+// error: an absolute 2^-25, far below the fp32 noise of a layer output.  Saturating
+// conversions: |v| > 65504 does not become inf.
+template <bool kRelu>
+__device__ __forceinline__ void x3_piece_fast(const float* v, const float4* __restrict__ bq4, float inv_s,
+                                              uint32_t* hi16, uint32_t* lo16) {
   const uint64_t is2 = pack_f32x2(inv_s, inv_s);
 #pragma unroll
   for (int j = 0; j < 32; j += 4) {
     const float4 bq = bq4[j >> 2];                  // constant bank, warp-uniform address
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      uint64_t r, t, d;
+      asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(pack_f32x2(v[j + 2 * h], v[j + 2 * h + 1])), "l"(is2),
+          "l"(h == 0 ? pack_f32x2(bq.x, bq.y) : pack_f32x2(bq.z, bq.w)));
+      asm("and.b64 %0, %1, 0xFFFFE000FFFFE000;" : "=l"(t) : "l"(r));
+      asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(r), "l"(t));
+      float t0, t1, d0, d1;
+      asm("mov.b64 {%0, %1}, %2;" : "=f"(t0), "=f"(t1) : "l"(t));
+      asm("mov.b64 {%0, %1}, %2;" : "=f"(d0), "=f"(d1) : "l"(d));
+      if (kRelu) {
+        asm("cvt.rn.relu.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(hi16[(j >> 1) + h]) : "f"(t1), "f"(t0));
+        asm("cvt.rn.relu.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(lo16[(j >> 1) + h]) : "f"(d1), "f"(d0));
+      } else {
+        asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(hi16[(j >> 1) + h]) : "f"(t1), "f"(t0));
+        asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(lo16[(j >> 1) + h]) : "f"(d1), "f"(d0));
+      }
+    }
+  }
+}
+// The layer that also feeds the alpha head (one per level) needs the activated fp32 values.
+__device__ __forceinline__ void x3_piece_adot(const float* v, const float4* __restrict__ bq4, float inv_s, bool relu,
+                                              const float4* __restrict__ aw4, float& alpha,
+                                              uint32_t* hi16, uint32_t* lo16) {
+  const uint64_t is2 = pack_f32x2(inv_s, inv_s);
+#pragma unroll
+  for (int j = 0; j < 32; j += 4) {
+    const float4 bq = bq4[j >> 2];
     uint64_t r0, r1;
     asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r0) : "l"(pack_f32x2(v[j], v[j + 1])), "l"(is2), "l"(pack_f32x2(bq.x, bq.y)));
     asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r1) : "l"(pack_f32x2(v[j + 2], v[j + 3])), "l"(is2), "l"(pack_f32x2(bq.z, bq.w)));
@@ -238,14 +276,24 @@ __device__ __forceinline__ void x3_piece(const float* v, const float4* __restric
     asm("mov.b64 {%0, %1}, %2;" : "=f"(t0), "=f"(t1) : "l"(r0));
     asm("mov.b64 {%0, %1}, %2;" : "=f"(t2), "=f"(t3) : "l"(r1));
     if (relu) { t0 = fmaxf(t0, 0.f); t1 = fmaxf(t1, 0.f); t2 = fmaxf(t2, 0.f); t3 = fmaxf(t3, 0.f); }
-    if (adot) {
-      const float4 w = aw4[j >> 2];
-      alpha = fmaf(t0, w.x, alpha); alpha = fmaf(t1, w.y, alpha);
-      alpha = fmaf(t2, w.z, alpha); alpha = fmaf(t3, w.w, alpha);
-    }
+    const float4 w = aw4[j >> 2];
+    alpha = fmaf(t0, w.x, alpha); alpha = fmaf(t1, w.y, alpha);
+    alpha = fmaf(t2, w.z, alpha); alpha = fmaf(t3, w.w, alpha);
     split_pair(t0, t1, hi16[j >> 1], lo16[j >> 1]);
     split_pair(t2, t3, hi16[(j >> 1) + 1], lo16[(j >> 1) + 1]);
   }
+}
+__device__ __forceinline__ void x3_piece(const float* v, const float4* __restrict__ bq4, float inv_s, bool relu,
+                                         bool adot, const float4* __restrict__ aw4, float& alpha,
+                                         uint32_t* hi16, uint32_t* lo16) {
+#ifdef NFB_X3_EXP_NOEPI
+#pragma unroll
+  for (int j = 0; j < 16; ++j) { hi16[j] = 0x3c003c00u; lo16[j] = 0u; }
+  return;
+#endif
+  if (adot) x3_piece_adot(v, bq4, inv_s, relu, aw4, alpha, hi16, lo16);
+  else if (relu) x3_piece_fast<true>(v, bq4, inv_s, hi16, lo16);
+  else x3_piece_fast<false>(v, bq4, inv_s, hi16, lo16);
 }
 
 // First chain of a unit: fence + 4 x (x_hi W_hi).  kTs: A from tensor memory (a = TMEM
@@ -376,9 +424,20 @@ __device__ __forceinline__ uint32_t issue_x3_tail(uint32_t d, uint64_t a_hi, uin
 #undef NFB_X3_TAIL_EPILOGUE
 
 // One 32-column piece of a layer's output (16 packed pairs per image) -> this thread's TMEM lane.
+// (NFB_X3_EXP_*: timing experiments of developer builds, garbage results.)
 __device__ __forceinline__ void tst_piece(uint32_t t_lane, int col, const uint32_t* hi16, const uint32_t* lo16) {
+#if !defined(NFB_X3_EXP_NOTMEM) && !defined(NFB_X3_EXP_NOEPI)
   tmem_st16(t_lane + kTmAHi + (uint32_t)(col >> 1), hi16);
   tmem_st16(t_lane + kTmALo + (uint32_t)(col >> 1), lo16);
+#endif
+}
+__device__ __forceinline__ void x3_ld32(uint32_t taddr, float* v) {
+#if !defined(NFB_X3_EXP_NOTMEM) && !defined(NFB_X3_EXP_NOEPI)
+  tmem_ld32(taddr, v);
+#else
+#pragma unroll
+  for (int j = 0; j < 32; ++j) v[j] = 1.f;
+#endif
 }
 
 // Row state owned by the two epilogue threads of a row for the lifetime of a tile.
@@ -475,6 +534,11 @@ field_x3_kernel(const __grid_constant__ TcProgram prog, const __grid_constant__ 
           const uint8_t* from = src + (size_t)u * bytes;
           mbar_wait(&bars->empty[sg], ph ^ 1, dead);
           tr.ev(si, u);
+#ifdef NFB_X3_EXP_NOFILL
+          // timing experiment (garbage results): only the first pass over the ring is copied
+          if (ti > 0 || si > first_step + 1) { if (elect_one()) mbar_arrive(&bars->full[sg]); __syncwarp();
+            if (++sg == kX3Slots) { sg = 0; ph ^= 1; } continue; }
+#endif
           if (elect_one()) {
             mbar_arrive_expect_tx(&bars->full[sg], bytes);
             if constexpr (kPair) {
@@ -649,14 +713,14 @@ field_x3_kernel(const __grid_constant__ TcProgram prog, const __grid_constant__ 
           tr.ev(si, 0);
           if (wide) {
             float va[32], vb[32];
-            tmem_ld32(t_lane + col0, va);
-            tmem_ld32(t_lane + col0 + 32, vb);
+            x3_ld32(t_lane + col0, va);
+            x3_ld32(t_lane + col0 + 32, vb);
             tmem_ld_wait();
             x3_piece(va, bias4 + (col0 >> 2), inv_s, relu, adot, cst.alpha4 + (col0 >> 2), row.alpha, ph, pl);
             x3_piece(vb, bias4 + (col0 >> 2) + 8, inv_s, relu, adot, cst.alpha4 + (col0 >> 2) + 8, row.alpha, ph + 16, pl + 16);
           } else {
             float va[32];
-            tmem_ld32(t_lane + col0, va);
+            x3_ld32(t_lane + col0, va);
             tmem_ld_wait();
             x3_piece(va, bias4 + (col0 >> 2), inv_s, relu, adot, cst.alpha4 + (col0 >> 2), row.alpha, ph, pl);
           }
@@ -681,24 +745,27 @@ field_x3_kernel(const __grid_constant__ TcProgram prog, const __grid_constant__ 
           tr.ev(si, 4);
           if (wide) {
             float va[32], vb[32];
-            tmem_ld32(t_lane + col1, va);
-            tmem_ld32(t_lane + col1 + 32, vb);
+            x3_ld32(t_lane + col1, va);
+            x3_ld32(t_lane + col1 + 32, vb);
             tmem_ld_wait();
+            tc_fence_before();
+            mbar_arrive(&bars->x_ready[1]);             // this accumulator may be overwritten (next step's chunk 1)
             x3_piece(va, bias4 + (col1 >> 2), inv_s, relu, adot, cst.alpha4 + (col1 >> 2), row.alpha, ph, pl);
             tst_piece(t_lane, col1, ph, pl);
             x3_piece(vb, bias4 + (col1 >> 2) + 8, inv_s, relu, adot, cst.alpha4 + (col1 >> 2) + 8, row.alpha, ph, pl);
             tst_piece(t_lane, col1 + 32, ph, pl);
           } else {
             float va[32];
-            tmem_ld32(t_lane + col1, va);
+            x3_ld32(t_lane + col1, va);
             tmem_ld_wait();
+            tc_fence_before();
+            mbar_arrive(&bars->x_ready[1]);
             x3_piece(va, bias4 + (col1 >> 2), inv_s, relu, adot, cst.alpha4 + (col1 >> 2), row.alpha, ph, pl);
             tst_piece(t_lane, col1, ph, pl);
           }
           if (adot && hs == 1) alpha_part[r] = row.alpha;   // read by the row's first thread at the rgb step
           tmem_st_wait();
           tc_fence_before();
-          mbar_arrive(&bars->x_ready[1]);
           mbar_arrive(&bars->x_ready[2]);
           tr.ev(si, 5);
         } else {
@@ -849,6 +916,9 @@ inline int run_field_x3(nfb_handle* h, int level, const FieldArgs& a, cudaStream
   if (fuse && (a.samples_per_ray % kTileRows != 0 || a.num_rows % a.samples_per_ray != 0))
     return fail("fused composite needs samples_per_ray to be a multiple of %d", kTileRows);
   const long long groups = fuse ? a.num_rows / a.samples_per_ray : tiles;
+#ifdef NFB_X3_EXP_NOPAIR
+  h->x3_pair_ok = 0;
+#endif
   if (groups >= (long long)h->sm_count && h->x3_pair_ok != 0) {
     // CTA pairs sharing the weight stream (see the kernel): worth it once every SM has work
     cudaLaunchConfig_t cfg = {};

@@ -106,7 +106,8 @@ struct nfb_handle {
   unsigned char* d_wpack = nullptr;   // bf16 weight units, shared-memory image
   float* d_aux = nullptr;             // fp32 biases + alpha head
   long long wpack_bytes = 0, aux_floats = 0;
-  struct TcPackJob { int level, step, chunk; int simt_w_off, ld, n, n0, k_total; std::vector<int> k_map; };
+  struct TcPackJob { int level, step, chunk; int simt_w_off, ld, n, n0, k_total; std::vector<int> k_map;
+                     std::vector<int> unit_pos; };   // fp16x3: issue-order position of each K-block's unit within the step
   std::vector<TcPackJob> tc_jobs;
   struct TcAuxJob { int src_off, count, stride, dst_off; };
   std::vector<TcAuxJob> tc_aux_jobs;

@@ -206,6 +206,46 @@ int nfb_train_value_and_grad(nfb_handle* h, int num_rays, const float* origins,
                              const float* rgb_target, int chunk_rays, float* const* grads,
                              const long long* numels, int count, float* loss_out, void* stream);
 
+/* Regularisers of training.train_step (training.py:138-147, 71-135, 176-212, 246-257). */
+enum { NFB_ELASTIC_LOG_SVALS = 0, NFB_ELASTIC_SVALS = 1, NFB_ELASTIC_JTJ = 2, NFB_ELASTIC_DIV = 3,
+       NFB_ELASTIC_DET = 4, NFB_ELASTIC_LOG_DET = 5 };
+typedef struct nfb_train_reg {
+  int use_elastic_loss;            /* training.py:143; applies to the coarse level (training.py:242-244) */
+  int elastic_reduce_method;       /* 0 = 'median' (the median-depth sample of each ray), 1 = 'weight' */
+  int elastic_loss_type;           /* NFB_ELASTIC_* = compute_elastic_loss's loss_type ('nr' unsupported) */
+  float elastic_loss_weight;       /* ScalarParams.elastic_loss_weight */
+  int use_warp_reg_loss;           /* training.py:147, both levels */
+  float warp_reg_loss_weight, warp_reg_loss_alpha, warp_reg_loss_scale;
+  int use_background_loss;         /* training.py:146 */
+  int num_background_points;
+  const float* background_points;        /* device (P,3): batch['background_points'] */
+  const unsigned* background_warp_ids;   /* device (P): the reference draws random.choice(key, model.warp_ids) */
+  const float* background_noise;         /* device (P,3) or NULL: noise_std * random.normal(key, points.shape) */
+  float background_loss_weight;          /* ScalarParams.background_loss_weight */
+} nfb_train_reg;
+
+/* nfb_train_value_and_grad plus the regularisers (reg may be NULL).  loss_out: 16 device floats
+ *   [0] rgb loss coarse  [1] rgb loss fine  [2] loss/elastic  [3] residual/elastic
+ *   [4] metric/jacobian_det  [5] metric/jacobian_div  [6] metric/jacobian_curl (means over the rows whose
+ *   Jacobian the loss uses: the reference averages these three over every coarse sample, training.py:214-222)
+ *   [7] loss/warp_reg coarse  [8] residual/warp_reg coarse  [9] loss/warp_reg fine  [10] residual fine
+ *   [11] background loss (unweighted mean)  [12] mean |warped - x| of the background points.
+ * The gradient is that of  rgb_coarse + rgb_fine + elastic_loss_weight * [2] + warp_reg_loss_weight *
+ * ([7] + [9]) + background_loss_weight * [11]  (training.py:176-212, 228-259).  Replaces
+ * jax.value_and_grad(_loss_fn) (training.py:263-264) with every regulariser of train_step. */
+int nfb_train_value_and_grad_reg(nfb_handle* h, int B, const float* origins, const float* directions,
+                                 const float* viewdirs, const unsigned* warp_id, const unsigned* app_id,
+                                 const unsigned* cam_id, float warp_alpha, const float* t_rand,
+                                 const float* u_rand, unsigned flags, const float* rgb_target,
+                                 int chunk_rays, const nfb_train_reg* reg, float* const* grads,
+                                 const long long* numels, int count, float* loss_out, void* stream);
+
+/* Jacobian of the warp field at free points: jacobian_out (P,3,3), J[i][j] = d warped_i / d point_j
+ * (jax.jacfwd(self.warp, argnums=0), warping.py:196-198, 385-387); warped_out (P,3) nullable.
+ * warp_id (P) GLO ids.  fp32, any precision mode of the handle (layer-wise tape kernels). */
+int nfb_warp_jacobian(nfb_handle* h, int P, const float* points, const unsigned* warp_id, float warp_alpha,
+                      float* warped_out, float* jacobian_out, void* stream);
+
 /* flax.optim.Adam.apply_gradient (training.py:268; beta1 0.9, beta2 0.999, eps 1e-8, no
  * weight decay are the Flax defaults the reference uses, train.py:219) on flat device
  * vectors of n floats; `step` counts from 1 (bias correction 1 - beta^step).  No handle. */

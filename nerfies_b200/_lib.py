@@ -19,8 +19,22 @@ SYMBOLS = [
     'nfb_set_profiling', 'nfb_field_time_ms', 'nfb_selftest_gemm', 'nfb_set_trace', 'nfb_selftest_microbench',
     'nfb_camera_rays', 'nfb_pixels_to_rays', 'nfb_selftest_gemm2', 'nfb_selftest_gemm3',
     'nfb_debug_provoke_timeout', 'nfb_set_time_alpha', 'nfb_train_value_and_grad', 'nfb_adam_step',
+    'nfb_train_value_and_grad_reg', 'nfb_warp_jacobian',
 ]
 
+class TrainReg(ctypes.Structure):
+  """nfb_train_reg (include/nerfies_b200.h)."""
+  _fields_ = [('use_elastic_loss', ctypes.c_int), ('elastic_reduce_method', ctypes.c_int),
+              ('elastic_loss_type', ctypes.c_int), ('elastic_loss_weight', ctypes.c_float),
+              ('use_warp_reg_loss', ctypes.c_int), ('warp_reg_loss_weight', ctypes.c_float),
+              ('warp_reg_loss_alpha', ctypes.c_float), ('warp_reg_loss_scale', ctypes.c_float),
+              ('use_background_loss', ctypes.c_int), ('num_background_points', ctypes.c_int),
+              ('background_points', ctypes.c_void_p), ('background_warp_ids', ctypes.c_void_p),
+              ('background_noise', ctypes.c_void_p), ('background_loss_weight', ctypes.c_float)]
+
+
+ELASTIC_TYPES = {'log_svals': 0, 'svals': 1, 'jtj': 2, 'div': 3, 'det': 4, 'log_det': 5}
+ELASTIC_REDUCE = {'median': 0, 'weight': 1}
 ACTIVATIONS = {'none': 0, 'relu': 1, 'elu': 2, 'leaky_relu': 3, 'tanh': 4,
                'sigmoid': 5, 'softplus': 6}
 WARP_TYPES = {None: 0, 'none': 0, 'translation': 1, 'se3': 2}
@@ -141,6 +155,11 @@ def load():
   lib.nfb_train_value_and_grad.argtypes = [vp, ci] + [vp] * 6 + [cf, vp, vp, cu, vp, ci, ctypes.POINTER(vp),
                                            ctypes.POINTER(ctypes.c_longlong), ci, vp, vp]
   lib.nfb_train_value_and_grad.restype = ci
+  lib.nfb_train_value_and_grad_reg.argtypes = [vp, ci] + [vp] * 6 + [cf, vp, vp, cu, vp, ci, vp, ctypes.POINTER(vp),
+                                               ctypes.POINTER(ctypes.c_longlong), ci, vp, vp]
+  lib.nfb_train_value_and_grad_reg.restype = ci
+  lib.nfb_warp_jacobian.argtypes = [vp, ci, vp, vp, cf, vp, vp, vp]
+  lib.nfb_warp_jacobian.restype = ci
   lib.nfb_adam_step.argtypes = [vp, vp, vp, vp, ctypes.c_longlong, cf, cf, cf, cf, ctypes.c_longlong, vp]
   lib.nfb_adam_step.restype = ci
   lib.nfb_set_time_alpha.argtypes = [vp, cf]

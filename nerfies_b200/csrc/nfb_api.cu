@@ -759,7 +759,8 @@ void nfb_destroy(nfb_handle* h) {
                    h->d_lower, h->d_upper, h->d_ulin, h->d_window, h->d_cond, h->d_zc, h->d_zf,
                    h->d_wc, h->d_samples, h->d_out_c, h->d_out_f, h->d_in};
   for (float* p : bufs) if (p) cudaFree(p);
-  float* tbufs[] = {h->d_tape, h->d_gpacked, h->d_gwarp, h->d_gapp, h->d_gcam, h->d_dcond, h->d_tr_out, h->d_tr_w, h->d_loss};
+  float* tbufs[] = {h->d_tape, h->d_gpacked, h->d_gwarp, h->d_gapp, h->d_gcam, h->d_dcond, h->d_tr_out, h->d_tr_w, h->d_loss,
+                    h->d_ttape, reinterpret_cast<float*>(h->d_sel)};
   for (float* p : tbufs) if (p) cudaFree(p);
   if (h->d_ids) cudaFree(h->d_ids);
   for (int l = 0; l < 2; ++l)

@@ -95,6 +95,8 @@ struct nfb_handle {
   float* d_tape = nullptr; long long tape_floats = 0;
   float *d_gpacked = nullptr, *d_gwarp = nullptr, *d_gapp = nullptr, *d_gcam = nullptr;
   float *d_dcond = nullptr, *d_tr_out = nullptr, *d_tr_w = nullptr, *d_loss = nullptr;
+  float* d_ttape = nullptr; long long ttape_floats = 0;     // tangent tape (train_reg.cuh)
+  int* d_sel = nullptr; long long sel_cap = 0;              // selected tape rows (median-depth samples)
   int x3_pair_ok = -1;                // fp16x3 CTA-pair launch: -1 unknown, 0 unavailable, n = co-resident clusters
   int debug_bits = 0;                 // FieldArgs::debug bits set through the test hook (abort-path test)
   long long* trace = nullptr;

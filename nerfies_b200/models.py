@@ -372,10 +372,18 @@ class NerfModel:
     uniform draws of the stratified path (used by the parity tests).
     """
     del deterministic, mutable  # unused by the reference's __call__ as well.
-    if return_warp_jacobian or self.use_warp_jacobian:
-      raise NotImplementedError(
-          'warp Jacobians (jax.jacfwd, warping.py:385-387) belong to the '
-          'training tier (SURVEY.md §8f #2) and are not implemented')
+    # models.py:345, 367: the coarse level returns Jacobians when either the call or the
+    # model asks for them, the fine level only when the call does.
+    jac_levels = []
+    if use_warp and self.use_warp:
+      if return_warp_jacobian or self.use_warp_jacobian:
+        jac_levels.append('coarse')
+      if return_warp_jacobian:
+        jac_levels.append('fine')
+    if jac_levels and (metadata_encoded or self.warp_metadata_encoder_type != 'glo'):
+      raise NotImplementedError("warp Jacobians: 'glo' warp metadata ids only")
+    want_points = return_points
+    return_points = return_points or bool(jac_levels)       # the Jacobian is taken at the sample points
     params = variables['params']
     warp_extra = warp_extra or {'alpha': 0.0, 'time_alpha': 0.0}
     alpha = float(warp_extra.get('alpha', 0.0))
@@ -481,10 +489,22 @@ class NerfModel:
         ret['weights'] = w
       if level in pts:
         z, wp = pts[level]
-        ret['points'] = origins[:, None, :] + z[:, :, None] * directions[:, None, :]
-        if use_warp:
-          ret['warped_points'] = wp
-        ret['z_vals'] = z
+        points = origins[:, None, :] + z[:, :, None] * directions[:, None, :]
+        if level in jac_levels:
+          # jax.jacfwd(self.warp)(points, ...) for every sample (warping.py:385-387, models.py:265-266)
+          S = z.shape[1]
+          flat = points.reshape(-1, 3).contiguous()
+          ids = warp_id[:, None].expand(B, S).reshape(-1).contiguous()
+          jac = torch.empty(B * S, 3, 3, device=dev)
+          with torch.cuda.device(dev):
+            _lib.check(lib.nfb_warp_jacobian(h, B * S, _ptr(flat), _ptr(ids), alpha, None, _ptr(jac),
+                                             _stream()))
+          ret['warp_jacobian'] = jac.reshape(B, S, 3, 3)
+        if want_points:
+          ret['points'] = points
+          if use_warp:
+            ret['warped_points'] = wp
+          ret['z_vals'] = z
       return ret
 
     if _packed:
@@ -560,9 +580,9 @@ class WarpField:
     are uploaded on every call whose tensors changed; with the subtree only, the
     non-warp parameters keep their last uploaded values (zeros if none were ever
     uploaded - the warp-only launch does not read them)."""
-    if return_jacobian:
-      raise NotImplementedError('warp Jacobian: training tier (SURVEY §8f #2)')
     m = self.model
+    if return_jacobian and (metadata_encoded or m.warp_metadata_encoder_type != 'glo'):
+      raise NotImplementedError("warp Jacobian: 'glo' warp metadata ids only")
     dev = m.device
     pts = _prep_f32(points, dev)
     shape = pts.shape
@@ -587,7 +607,13 @@ class WarpField:
       _lib.check(hd.lib.nfb_warp_forward(
           hd.h, P, _ptr(pts), _ptr(ids), float(extra.get('alpha', 0.0)), flags,
           _ptr(out), _stream()))
-    return {'warped_points': out.reshape(shape)}
+      ret = {'warped_points': out.reshape(shape)}
+      if return_jacobian:                                  # warping.py:385-387
+        jac = torch.empty(P, 3, 3, device=dev)
+        _lib.check(hd.lib.nfb_warp_jacobian(hd.h, P, _ptr(pts), _ptr(ids), float(extra.get('alpha', 0.0)),
+                                            None, _ptr(jac), _stream()))
+        ret['jacobian'] = jac.reshape(*shape[:-1], 3, 3)
+    return ret
 
 
 # ---------------------------------------------------------------------------

@@ -11,8 +11,12 @@ vector), and flax.optim.Adam's update.  Gradients come from
 `nfb_train_value_and_grad` (hand-written fp32 kernels, include/nerfies_b200.h), the
 update from `nfb_adam_step`; torch is the allocator and the NCCL binding.
 
-Not implemented: the elastic loss (needs the warp Jacobian's backward), the warp
-regulariser, and the background loss; asking for them raises NotImplementedError.
+The regularisers of train_step - the elastic loss on the warp Jacobian (training.py:71-115,
+176-193), the warp regulariser (training.py:194-207) and the background loss
+(training.py:118-135, 246-257) - are part of the same native call
+(`nfb_train_value_and_grad_reg`).  The reference draws the background points'
+warp ids and noise with jax.random (training.py:122-126); here they come from a torch
+generator seeded by `rng_key` (or are passed in the batch): same distribution, different stream.
 """
 import ctypes
 import dataclasses
@@ -91,9 +95,44 @@ def create_train_state(model, params, warp_alpha=0.0, time_alpha=0.0):
   return model_utils.TrainState(opt, warp_alpha=warp_alpha, time_alpha=time_alpha)
 
 
+def make_reg(model, scalar_params=None, use_elastic_loss=False, elastic_reduce_method='median',
+             elastic_loss_type='log_svals', use_background_loss=False, use_warp_reg_loss=False,
+             background_points=None, background_warp_ids=None, background_noise=None):
+  """The regulariser switches of train_step (training.py:138-147) + ScalarParams -> nfb_train_reg.
+  Returns (TrainReg, keepalive list of the device tensors it points to)."""
+  sp = scalar_params
+  reg = _lib.TrainReg()
+  keep = []
+  if elastic_loss_type not in _lib.ELASTIC_TYPES:
+    raise NotImplementedError(f'elastic loss type {elastic_loss_type!r} (the reference notes that '
+                              "'nr' produces NaNs, training.py:59)")
+  reg.use_elastic_loss = int(bool(use_elastic_loss))
+  reg.elastic_reduce_method = _lib.ELASTIC_REDUCE[elastic_reduce_method]
+  reg.elastic_loss_type = _lib.ELASTIC_TYPES[elastic_loss_type]
+  reg.elastic_loss_weight = float(sp.elastic_loss_weight) if sp else 0.0
+  reg.use_warp_reg_loss = int(bool(use_warp_reg_loss))
+  reg.warp_reg_loss_weight = float(sp.warp_reg_loss_weight) if sp else 0.0
+  reg.warp_reg_loss_alpha = float(sp.warp_reg_loss_alpha) if sp else -2.0
+  reg.warp_reg_loss_scale = float(sp.warp_reg_loss_scale) if sp else 0.001
+  reg.use_background_loss = int(bool(use_background_loss))
+  if use_background_loss:
+    dev = model.device
+    pts = _prep_f32(background_points, dev).reshape(-1, 3).contiguous()
+    ids = _prep_ids(torch.as_tensor(background_warp_ids).reshape(pts.shape[0], -1), dev)
+    noise = None if background_noise is None else _prep_f32(background_noise, dev).reshape(-1, 3).contiguous()
+    keep += [pts, ids, noise]
+    reg.num_background_points = pts.shape[0]
+    reg.background_points = pts.data_ptr()
+    reg.background_warp_ids = ids.data_ptr()
+    reg.background_noise = None if noise is None else noise.data_ptr()
+    reg.background_loss_weight = float(sp.background_loss_weight) if sp else 0.0
+  return reg, keep
+
+
 def value_and_grad(model, params, batch, warp_extra, rngs=None, chunk_rays=256, t_rand=None,
-                   u_rand=None, grads=None):
-  """(loss dict, flat gradient) of the photometric loss (training.py:171-175, 214-244, 263-264).
+                   u_rand=None, grads=None, reg=None):
+  """(loss dict, flat gradient) of the training loss (training.py:171-259, 263-264): the
+  photometric terms and, with `reg` (make_reg), the regularisers.
   `grads` (flat, zeroed by the caller) may be passed to accumulate into."""
   dev = model.device
   origins = _prep_f32(batch['origins'], dev)
@@ -119,14 +158,22 @@ def value_and_grad(model, params, batch, warp_extra, rngs=None, chunk_rays=256, 
   for i, k in enumerate(numels):
     ptrs[i] = grads.data_ptr() + 4 * off
     off += k
-  loss = torch.zeros(2, device=dev)
+  loss = torch.zeros(16, device=dev)
+  reg_struct, keep = reg if isinstance(reg, tuple) else (reg, None)
   with torch.cuda.device(dev):
-    _lib.check(hd.lib.nfb_train_value_and_grad(
+    _lib.check(hd.lib.nfb_train_value_and_grad_reg(
         hd.h, B, _ptr(origins), _ptr(directions), _ptr(viewdirs), _ptr(warp_id), _ptr(app_id),
         _ptr(cam_id), float((warp_extra or {}).get('alpha', 0.0)), _ptr(t_rand), _ptr(u_rand), 0,
-        _ptr(target), int(chunk_rays), ptrs, (ctypes.c_longlong * n)(*numels), n, _ptr(loss),
-        _stream()))
-  return {'coarse': loss[0], 'fine': loss[1]}, grads
+        _ptr(target), int(chunk_rays), ctypes.byref(reg_struct) if reg_struct is not None else None,
+        ptrs, (ctypes.c_longlong * n)(*numels), n, _ptr(loss), _stream()))
+  del keep
+  out = {'coarse': loss[0], 'fine': loss[1]}
+  if reg_struct is not None:
+    out.update({'elastic': loss[2], 'elastic_residual': loss[3], 'jacobian_det': loss[4],
+                'jacobian_div': loss[5], 'jacobian_curl': loss[6], 'warp_reg_coarse': loss[7],
+                'warp_reg_residual_coarse': loss[8], 'warp_reg_fine': loss[9],
+                'warp_reg_residual_fine': loss[10], 'background': loss[11]})
+  return out, grads
 
 
 def grads_to_tree(model, grads):
@@ -152,11 +199,22 @@ def train_step(model, rng_key, state, batch, scalar_params, use_elastic_loss=Fal
 
   timings (optional dict) receives 'value_and_grad_ms', 'all_reduce_ms', 'adam_ms' measured
   with CUDA events on the current stream."""
-  del elastic_reduce_method, elastic_loss_type
+  reg = None
   if use_elastic_loss or use_warp_reg_loss or use_background_loss:
-    raise NotImplementedError(
-        'elastic / warp-reg / background regularisers (training.py:71-135, 187-212, 246-257) are '
-        'not implemented: they need the backward of the warp Jacobian (SURVEY §8f #2)')
+    bg = {}
+    if use_background_loss:
+      # training.py:122-126: ids ~ random.choice(key, model.warp_ids), noise ~ noise_std * N(0, 1)
+      pts = torch.as_tensor(batch['background_points']).reshape(-1, 3)
+      gen = torch.Generator().manual_seed(int(rng_key) if not isinstance(rng_key, torch.Generator) else rng_key.seed())
+      warp_ids = torch.as_tensor(list(model.warp_ids), dtype=torch.int64)
+      bg['background_points'] = pts
+      bg['background_warp_ids'] = batch.get(
+          'background_warp_ids', warp_ids[torch.randint(len(warp_ids), (pts.shape[0],), generator=gen)])
+      bg['background_noise'] = batch.get(
+          'background_noise',
+          scalar_params.background_noise_std * torch.randn(pts.shape[0], 3, generator=gen))
+    reg = make_reg(model, scalar_params, use_elastic_loss, elastic_reduce_method, elastic_loss_type,
+                   use_background_loss, use_warp_reg_loss, **bg)
   opt = state.optimizer
   ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)] if timings is not None else None
   if ev:
@@ -164,11 +222,27 @@ def train_step(model, rng_key, state, batch, scalar_params, use_elastic_loss=Fal
   params = opt.target['model']
   model.invalidate_params()     # the Adam kernel rewrote the flat vector under the views
   losses, grads = value_and_grad(model, params, batch, state.warp_extra,
-                                 rngs={'coarse': rng_key, 'fine': rng_key}, chunk_rays=chunk_rays)
+                                 rngs={'coarse': rng_key, 'fine': rng_key}, chunk_rays=chunk_rays, reg=reg)
   if ev:
     ev[1].record()
-  stats = {lv: {'loss/rgb': l, 'loss/total': l, 'metric/psnr': -10.0 * torch.log10(l)}
-           for lv, l in losses.items()}
+  # stats of _compute_loss_and_stats (training.py:171-226)
+  stats = {lv: {'loss/rgb': losses[lv], 'loss/total': losses[lv], 'metric/psnr': -10.0 * torch.log10(losses[lv])}
+           for lv in ('coarse', 'fine') if lv in losses}
+  if use_elastic_loss:
+    c = stats['coarse']
+    c['loss/elastic'] = losses['elastic']
+    c['residual/elastic'] = losses['elastic_residual']
+    c['loss/total'] = c['loss/total'] + scalar_params.elastic_loss_weight * losses['elastic']
+    c['metric/jacobian_det'] = losses['jacobian_det']
+    c['metric/jacobian_div'] = losses['jacobian_div']
+    c['metric/jacobian_curl'] = losses['jacobian_curl']
+  if use_warp_reg_loss:
+    for lv in stats:
+      stats[lv]['loss/warp_reg'] = losses['warp_reg_' + lv]
+      stats[lv]['residual/warp_reg'] = losses['warp_reg_residual_' + lv]
+      stats[lv]['loss/total'] = stats[lv]['loss/total'] + scalar_params.warp_reg_loss_weight * losses['warp_reg_' + lv]
+  if use_background_loss:
+    stats['background_loss'] = losses['background']
   if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
     # jax.lax.pmean(grad, 'batch') (training.py:266): one collective over the flat vector
     dist.all_reduce(grads)

@@ -35,7 +35,26 @@ class JArray(_np.ndarray):
     return _np.true_divide(self, o)
 
 
+_X64 = [False]
+
+
+class x64:
+  """Context manager: float64 results are kept (jax.config jax_enable_x64); used by the
+  numerical jacfwd stand-in only."""
+
+  def __enter__(self):
+    self.prev = _X64[0]
+    _X64[0] = True
+
+  def __exit__(self, *exc):
+    _X64[0] = self.prev
+
+
 def _narrow(x):
+  if _X64[0]:
+    if isinstance(x, _np.ndarray) and not isinstance(x, JArray):
+      x = x.view(JArray)
+    return x
   if isinstance(x, _np.ndarray) or isinstance(x, _np.generic):
     if x.dtype == _np.float64:
       x = x.astype(_np.float32)
@@ -127,6 +146,15 @@ def block(x):
 
 class _Linalg:
   @staticmethod
+  def svd(x, compute_uv=True, full_matrices=True):
+    r = _np.linalg.svd(x, compute_uv=compute_uv, full_matrices=full_matrices)
+    return tuple(_narrow(v) for v in r) if compute_uv else _narrow(r)
+
+  @staticmethod
+  def det(x):
+    return _narrow(_np.linalg.det(x))
+
+  @staticmethod
   def norm(x, axis=None, keepdims=False):
     # jnp.linalg.norm: sqrt(sum(x*x)) in the array's dtype.
     x = array(x)
@@ -141,5 +169,15 @@ for _name in ['linspace', 'eye', 'sin', 'cos', 'exp', 'log', 'sqrt', 'tanh',
               'logical_xor', 'ones_like', 'zeros_like', 'full_like', 'arange',
               'abs', 'logaddexp', 'transpose', 'matmul', 'dot', 'mean',
               'square', 'power', 'isnan', 'isfinite', 'all', 'any', 'take',
-              'log10', 'floor', 'diag', 'trace']:
+              'log10', 'floor', 'diag', 'trace', 'log1p', 'expm1', 'greater_equal',
+              'take_along_axis', 'cross', 'argsort', 'sign']:
   globals()[_name] = _wrap(getattr(_np, _name))
+
+
+class _FInfo:
+  def __init__(self, dtype):
+    self.eps = _np.float32(_np.finfo(dtype).eps)
+
+
+def finfo(dtype):
+  return _FInfo(dtype)

@@ -643,6 +643,170 @@ def pdf_cdf_residual(bins: Tensor, weights: Tensor, z_samples: Tensor,
 
 
 # --------------------------------------------------------------------------
+# warp Jacobian, elastic / warp-reg / background regularisers
+# --------------------------------------------------------------------------
+def warp_jacobian(params, spec: OracleSpec, points: Tensor, metadata: Tensor,
+                  alpha: float, time_alpha: Optional[float] = None,
+                  create_graph: bool = False) -> Tensor:
+  """jax.jacfwd(self.warp, argnums=0)(points, metadata_embed, extra)
+  (warping.py:196-198, 385-387), vmapped over the batch dimensions by
+  model_utils.vmap_module (warping.py:46-57): J[..., i, j] = d warped_i / d point_j.
+  `points` (..., 3), `metadata` (..., 1) ids.  Differentiable w.r.t. the
+  parameters when create_graph=True (double backward through autograd)."""
+  shape = points.shape[:-1]
+  pts = points.reshape(-1, 3).detach().clone().requires_grad_(True)
+  meta = metadata.reshape(-1, metadata.shape[-1])
+  embed = encode_warp_metadata(params, spec, meta, time_alpha, pts.dtype)
+  warp = se3_field_warp if spec.warp_field_type == 'se3' else translation_field_warp
+  warped = warp(params, spec, pts, embed, alpha)
+  rows = []
+  for i in range(3):
+    g, = torch.autograd.grad(warped[:, i].sum(), pts, create_graph=create_graph,
+                             retain_graph=True)
+    rows.append(g)
+  return torch.stack(rows, dim=-2).reshape(*shape, 3, 3)
+
+
+def log1p_safe(x: Tensor) -> Tensor:
+  """utils.py:244-246."""
+  return torch.log1p(torch.clamp(x, max=3e37))
+
+
+def expm1_safe(x: Tensor) -> Tensor:
+  """utils.py:254-256."""
+  return torch.expm1(torch.clamp(x, max=87.5))
+
+
+def general_loss_with_squared_residual(squared_x: Tensor, alpha: float,
+                                       scale: float) -> Tensor:
+  """utils.py:264-331 (Barron's general robust loss on a squared residual)."""
+  eps = float(np.finfo(np.float32).eps)
+  x = squared_x / (scale ** 2)
+  if alpha == -math.inf:
+    loss = -torch.expm1(-0.5 * x)
+  elif alpha == 0:
+    loss = log1p_safe(0.5 * x)
+  elif alpha == 2:
+    loss = 0.5 * x
+  elif alpha == math.inf:
+    loss = expm1_safe(0.5 * x)
+  else:
+    beta_safe = max(eps, abs(alpha - 2.0))
+    alpha_safe = (1.0 if alpha >= 0 else -1.0) * max(eps, abs(alpha))
+    loss = (beta_safe / alpha_safe) * (torch.pow(x / beta_safe + 1.0, 0.5 * alpha) - 1.0)
+  return scale * loss
+
+
+def jacobian_to_curl(jacobian: Tensor) -> Tensor:
+  """utils.py:71-84."""
+  return torch.stack([jacobian[..., 2, 1] - jacobian[..., 1, 2],
+                      jacobian[..., 0, 2] - jacobian[..., 2, 0],
+                      jacobian[..., 1, 0] - jacobian[..., 0, 1]], dim=-1)
+
+
+def jacobian_to_div(jacobian: Tensor) -> Tensor:
+  """utils.py:87-91: trace(J) - 3."""
+  return jacobian[..., 0, 0] + jacobian[..., 1, 1] + jacobian[..., 2, 2] - 3.0
+
+
+def nearest_rotation_svd(matrix: Tensor, eps: float = 1e-6) -> Tensor:
+  """training.py:57-68."""
+  u, _, vh = torch.linalg.svd(matrix + eps, full_matrices=False)
+  det = torch.linalg.det(u @ vh)
+  m = torch.diag_embed(torch.stack([torch.ones_like(det), torch.ones_like(det), det], dim=-1))
+  return u @ m @ vh
+
+
+def compute_elastic_loss(jacobian: Tensor, eps: float = 1e-6,
+                         loss_type: str = 'log_svals') -> Tuple[Tensor, Tensor]:
+  """training.py:71-115, batched over the leading dimensions (the reference vmaps it
+  twice, training.py:180).  Returns (loss, residual)."""
+  if loss_type == 'log_svals':
+    svals = torch.linalg.svdvals(jacobian)
+    log_svals = torch.log(torch.clamp(svals, min=eps))
+    sq_residual = torch.sum(log_svals ** 2, dim=-1)
+  elif loss_type == 'svals':
+    svals = torch.linalg.svdvals(jacobian)
+    sq_residual = torch.sum((svals - 1.0) ** 2, dim=-1)
+  elif loss_type == 'jtj':
+    jtj = jacobian @ jacobian.transpose(-1, -2)
+    sq_residual = ((jtj - torch.eye(3, dtype=jacobian.dtype)) ** 2).sum(dim=(-1, -2)) / 4.0
+  elif loss_type == 'div':
+    sq_residual = jacobian_to_div(jacobian) ** 2
+  elif loss_type == 'det':
+    sq_residual = (torch.linalg.det(jacobian) - 1.0) ** 2
+  elif loss_type == 'log_det':
+    sq_residual = torch.log(torch.clamp(torch.linalg.det(jacobian), min=eps)) ** 2
+  elif loss_type == 'nr':
+    rot = nearest_rotation_svd(jacobian)
+    sq_residual = torch.sum((jacobian - rot) ** 2, dim=(-1, -2))
+  else:
+    raise NotImplementedError(f'Unknown elastic loss type {loss_type!r}')
+  residual = torch.sqrt(sq_residual)
+  loss = general_loss_with_squared_residual(sq_residual, alpha=-2.0, scale=0.03)
+  return loss, residual
+
+
+def compute_opaqueness_mask(weights: Tensor, depth_threshold: float = 0.5) -> Tensor:
+  """model_utils.py:218-239."""
+  opaqueness = torch.cumsum(weights, dim=-1) >= depth_threshold
+  padded = torch.cat([torch.zeros_like(opaqueness[..., :1]), opaqueness[..., :-1]], dim=-1)
+  return torch.logical_xor(opaqueness, padded)
+
+
+def compute_depth_index(weights: Tensor, depth_threshold: float = 0.5) -> Tensor:
+  """model_utils.py:242-245: argmax of the mask (0 when the ray never reaches the threshold)."""
+  return torch.argmax(compute_opaqueness_mask(weights, depth_threshold).to(torch.int32), dim=-1)
+
+
+def compute_background_loss(params, spec: OracleSpec, points: Tensor, metadata: Tensor,
+                            point_noise: Tensor, warp_alpha: float, alpha: float = -2.0,
+                            scale: float = 0.001, time_alpha: Optional[float] = None) -> Tensor:
+  """training.py:118-135 with the random draws supplied by the caller: `metadata` (P,1)
+  = random.choice(key, warp_ids), `point_noise` (P,3) = noise_std * random.normal."""
+  pts = points + point_noise
+  warped = warp_field_apply(params['warp_field'], spec, pts, metadata, warp_alpha,
+                            False, time_alpha)
+  sq_residual = torch.sum((warped - pts) ** 2, dim=-1)
+  return general_loss_with_squared_residual(sq_residual, alpha=alpha, scale=scale)
+
+
+def level_regularisers(params, spec: OracleSpec, out: Dict[str, Tensor], rays_dict,
+                       warp_alpha: float, use_elastic_loss: bool = False,
+                       elastic_reduce_method: str = 'median', elastic_loss_type: str = 'log_svals',
+                       use_warp_reg_loss: bool = False, warp_reg_loss_alpha: float = -2.0,
+                       warp_reg_loss_scale: float = 0.001, create_graph: bool = True
+                       ) -> Dict[str, Tensor]:
+  """The regulariser terms of _compute_loss_and_stats (training.py:171-212) for one level's
+  `out` (render_level(..., return_points) output: 'points', 'warped_points', 'weights')."""
+  res = {}
+  weights = out['weights'].detach()                               # lax.stop_gradient
+  if use_elastic_loss:
+    B, S = weights.shape
+    meta = rays_dict['metadata']['warp'][:, None, :].expand(B, S, 1)
+    pts = out['points']
+    if elastic_reduce_method == 'median':
+      idx = compute_depth_index(weights)                          # training.py:184-188
+      pts = torch.gather(pts, 1, idx[:, None, None].expand(B, 1, 3))
+      meta = meta[:, :1]
+    jac = warp_jacobian(params['warp_field'], spec, pts, meta, warp_alpha, create_graph=create_graph)
+    loss, residual = compute_elastic_loss(jac, loss_type=elastic_loss_type)
+    if elastic_reduce_method == 'weight':
+      loss = weights * loss
+    res['loss/elastic'] = loss.sum(dim=-1).mean()
+    res['residual/elastic'] = residual.mean()
+    res['jacobian'] = jac
+  if use_warp_reg_loss:
+    idx = compute_depth_index(weights)
+    warp_mag = ((out['points'] - out['warped_points']) ** 2).sum(dim=-1)
+    r = torch.gather(warp_mag, 1, idx[:, None])
+    res['loss/warp_reg'] = general_loss_with_squared_residual(
+        r, alpha=warp_reg_loss_alpha, scale=warp_reg_loss_scale).mean()
+    res['residual/warp_reg'] = torch.sqrt(r).mean()
+  return res
+
+
+# --------------------------------------------------------------------------
 # R12  parameter construction with the reference initialisers
 # --------------------------------------------------------------------------
 def tree_to(tree, dtype):

@@ -814,11 +814,17 @@ inline int tc_fail(const char* what) {
 // the "phase B" K-blocks: the MMAs that overlap the previous chunk-1 epilogue are n_chunks x
 // |A| units instead of |A|, and the chunk-0 accumulator completes two units before the end of
 // the step so that its epilogue overlaps the tail.  Returns the number of units.
+// Activation blocks >= this index are written by the SECOND instalment of a hidden step's
+// epilogue (chunk 1 of a two-chunk step; columns 64.. of a one-chunk 128-wide step).
+inline int x3_split_of(const TcStep& prev) {
+  if (prev.epi != kEpiHidden) return 99;
+  return prev.n_chunks == 2 ? prev.chunk_n / kBlockK : 1;
+}
 inline int x3_unit_order(const TcProgram& tp, int si, int* oc, int* okb) {
   const TcStep& t = tp.steps[si];
   const bool after_heads = si > 0 && tp.steps[si - 1].epi != kEpiHidden;
   int split = 99;
-  if (si > 0 && !after_heads && tp.steps[si - 1].n_chunks == 2) split = tp.steps[si - 1].chunk_n / kBlockK;
+  if (si > 0 && !after_heads) split = x3_split_of(tp.steps[si - 1]);
   int n = 0;
   for (int phase = 0; phase < 2; ++phase)
     for (int c = 0; c < t.n_chunks; ++c)
@@ -865,6 +871,9 @@ inline int build_tc_program(nfb_handle* h, int level, long long* wbytes, long lo
     if (epi == kEpiHidden) {
       if (st.n != 128 && st.n != 256) return tc_fail("hidden widths must be 128 or 256");
       t.n_chunks = 2; t.chunk_n = st.n / 2;
+      // fp16x3: a 128-wide layer is ONE chunk of N = 128 (half the commits of two N = 64 chunks and
+      // full-rate MMAs); its epilogue hands the output over in two 64-column instalments
+      if (x3 && st.n == 128) { t.n_chunks = 1; t.chunk_n = 128; }
       if (st.act != kRelu && st.act != kNone) return tc_fail("hidden activation other than relu");
       t.relu = st.act == kRelu;
       t.kb_free = -1;
@@ -950,7 +959,7 @@ inline int build_tc_program(nfb_handle* h, int level, long long* wbytes, long lo
       int oc[16], okb[16];
       const int n = x3_unit_order(tp, si, oc, okb);
       const bool after_heads = si > 0 && tp.steps[si - 1].epi != kEpiHidden;
-      const int split = (si > 0 && !after_heads && tp.steps[si - 1].n_chunks == 2) ? tp.steps[si - 1].chunk_n / kBlockK : 99;
+      const int split = (si > 0 && !after_heads) ? x3_split_of(tp.steps[si - 1]) : 99;
       if (tp.n_units + n > kMaxTcUnits) return tc_fail("too many weight units");
       const int first = tp.n_units;
       int last_of_chunk[2] = {-1, -1}, first_of_chunk[2] = {-1, -1}, first_late = -1, last_low = -1;
@@ -977,12 +986,13 @@ inline int build_tc_program(nfb_handle* h, int level, long long* wbytes, long lo
         // x_ready[1] = "the previous chunk-1 epilogue has read its accumulator" (the first MMA of this step's
         // chunk 1 overwrites it), x_ready[2] = "... has stored its outputs" (the phase-B K-blocks)
         if (t.n_chunks == 2 && i == first_of_chunk[1]) u.flags |= kUWaitX1;
+        if (t.n_chunks == 1 && i == 0) u.flags |= kUWaitX1;
         if (i == first_late) u.flags |= kUWaitX2;
         if (t.n_chunks == 2 && i == (last_low >= 0 ? last_low : 0)) u.flags |= kUCommitXFree;
       }
       tp.units[first].flags |= kUWaitX0;
       TcUnit& last = tp.units[tp.n_units - 1];
-      if (t.n_chunks != 2) last.flags |= kUWaitX1;     // every phase is consumed before the final commit
+
       if (first_late < 0) last.flags |= kUWaitX2;
       last.flags |= kUStepEnd;
       // issue-order position of every (chunk, K-block): the weight units are packed in that order

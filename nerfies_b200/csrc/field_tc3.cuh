@@ -298,10 +298,36 @@ __device__ __forceinline__ void x3_piece(const float* v, const float4* __restric
 
 // First chain of a unit: fence + 4 x (x_hi W_hi).  kTs: A from tensor memory (a = TMEM
 // address, K steps of 8 columns) or from shared memory (a = descriptor, K steps of 32 bytes).
+// NFB_X3_COLLECT (A/B build): K-step-major order inside a unit so that x_hi[k] is read from tensor
+// memory once for its two products (collector::a::fill, then ::lastuse):
+//   for k: x_hi[k] W_hi[k] (fill), x_hi[k] W_lo[k] (lastuse), x_lo[k] W_hi[k]
+#ifdef NFB_X3_COLLECT
+constexpr bool kCollect = true;
+#else
+constexpr bool kCollect = false;
+#endif
 template <bool kTs>
-__device__ __forceinline__ void issue_x3_head(uint32_t d, uint64_t a_hi, uint64_t b_hi, uint32_t idesc,
-                                              uint32_t accumulate) {
-  if constexpr (kTs) {
+__device__ __forceinline__ void issue_x3_head(uint32_t d, uint64_t a_hi, uint64_t a_lo, uint64_t b_hi, uint64_t b_lo,
+                                              uint32_t idesc, uint32_t accumulate) {
+  if constexpr (kTs && kCollect) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred pacc, pt;\n\t"
+        ".reg .b32 h1;\n\t"
+        ".reg .b64 bh1;\n\t"
+        "tcgen05.fence::after_thread_sync;\n\t"
+        "setp.ne.b32 pacc, %6, 0;\n\t"
+        "setp.eq.b32 pt, 0, 0;\n\t"
+        "add.u32 h1, %1, 8;\n\t"
+        "add.u64 bh1, %3, 2;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16.collector::a::fill [%0], [%1], %3, %5, pacc;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16.collector::a::lastuse [%0], [%1], %4, %5, pt;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%2], %3, %5, pt;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16.collector::a::fill [%0], [h1], bh1, %5, pt;\n\t"
+        "}"
+        ::"r"(d), "r"((uint32_t)a_hi), "r"((uint32_t)a_lo), "l"(b_hi), "l"(b_lo), "r"(idesc), "r"(accumulate)
+        : "memory");
+  } else if constexpr (kTs) {
     asm volatile(
         "{\n\t"
         ".reg .pred pacc, pt;\n\t"
@@ -322,6 +348,7 @@ __device__ __forceinline__ void issue_x3_head(uint32_t d, uint64_t a_hi, uint64_
   } else {
     issue_half0(d, a_hi, b_hi, idesc, accumulate);
   }
+  (void)a_lo; (void)b_lo;
 }
 
 // Second and third MMA chains of a unit plus everything that follows them:
@@ -369,7 +396,31 @@ __device__ __forceinline__ uint32_t issue_x3_tail(uint32_t d, uint64_t a_hi, uin
                                                   uint32_t par_w, uint32_t probe_x0, uint32_t probe_x1,
                                                   uint32_t probe_x2, uint32_t par_x) {
   uint32_t out;
-  if constexpr (kTs) {
+  if constexpr (kTs && kCollect) {
+    asm volatile(
+        "{\n\t"
+        ".reg .b32 l1, l2, l3, h1, h2, h3;\n\t"
+        ".reg .b64 bh1, bh2, bh3, bl1, bl2, bl3;\n\t"
+        NFB_X3_TAIL_PROLOGUE
+        "add.u32 l1, %3, 8;\n\t add.u32 l2, %3, 16;\n\t add.u32 l3, %3, 24;\n\t"
+        "add.u32 h1, %2, 8;\n\t add.u32 h2, %2, 16;\n\t add.u32 h3, %2, 24;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16.collector::a::lastuse [%1], [h1], bl1, %6, pt;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%1], [l1], bh1, %6, pt;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16.collector::a::fill [%1], [h2], bh2, %6, pt;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16.collector::a::lastuse [%1], [h2], bl2, %6, pt;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%1], [l2], bh2, %6, pt;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16.collector::a::fill [%1], [h3], bh3, %6, pt;\n\t"
+        NFB_X3_TAIL_PROBES
+        "tcgen05.mma.cta_group::1.kind::f16.collector::a::lastuse [%1], [h3], bl3, %6, pt;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%1], [l3], bh3, %6, pt;\n\t"
+        NFB_X3_TAIL_EPILOGUE
+        "}"
+        : "=r"(out)
+        : "r"(d), "r"((uint32_t)a_hi), "r"((uint32_t)a_lo), "l"(b_hi), "l"(b_lo), "r"(idesc), "r"(bar_empty),
+          "r"(bar_xfree), "r"(bar_acc), "r"(probe_w), "r"(par_w), "r"(probe_x0), "r"(probe_x1),
+          "r"(probe_x2), "r"(par_x), "h"((uint16_t)0x3), "r"(kMulticastRelease ? 1u : 0u)
+        : "memory");
+  } else if constexpr (kTs) {
     asm volatile(
         "{\n\t"
         ".reg .b32 l1, l2, l3, h1, h2, h3;\n\t"
@@ -592,15 +643,16 @@ field_x3_kernel(const __grid_constant__ TcProgram prog, const __grid_constant__ 
             if (!(ready & 1)) mbar_wait_issuer(&bars->full[sg], wph, dead);
           }
           const bool ts = (c0.x & kUnitATmem) != 0;
-          if (ts) issue_x3_head<true>(d0, ad0, bd, c0.w, flags & kUAccum);     // x_hi W_hi
-          else issue_x3_head<false>(d0, ad0, bd, c0.w, flags & kUAccum);
+          const uint64_t a_lo = a_op(c0.y);
+          const uint64_t b_lo = bd + (uint64_t)(c1.z >> 16);    // W_lo follows W_hi inside the slot
+          if (ts) issue_x3_head<true>(d0, ad0, a_lo, bd, b_lo, c0.w, flags & kUAccum);     // x_hi W_hi
+          else issue_x3_head<false>(d0, ad0, a_lo, bd, b_lo, c0.w, flags & kUAccum);
           // ---- bookkeeping while those MMAs execute ----
           if (++un >= u_end) un -= n_u;
           const uint4 f0 = utab[2 * un], f1 = utab[2 * un + 1];          // table entry two units ahead
           const uint32_t nsg = sg + 1 == kX3Slots ? 0u : sg + 1;
           const uint32_t nwph = wph ^ (nsg == 0 ? 1u : 0u);
           const uint32_t nxr = xr + ((flags & kUStepEnd) ? 1u : 0u);
-          const uint64_t a_lo = a_op(c0.y);
           const uint32_t px0 = (c1.z & 2) ? b_x0 : 0u, px1 = (c1.z & 4) ? b_x1 : 0u;
           const uint32_t px2 = (c1.z & 8) ? b_x2 : 0u;
           const uint32_t d_cur = d0, idesc = c0.w, bar_e = b_empty + sg * 8;
@@ -609,7 +661,6 @@ field_x3_kernel(const __grid_constant__ TcProgram prog, const __grid_constant__ 
           bd = desc_hi | (uint64_t)(st_lo + nsg * (kX3SlotBytes >> 4));
           ad0 = a_op(n0.x);
           // W_lo follows W_hi inside the slot: chunk_n rows x 128 B further (c1.z bits 16..)
-          const uint64_t b_lo = bd_cur + (uint64_t)(c1.z >> 16);
           const uint32_t bar_x = (flags & kUCommitXFree) ? b_xfree : 0u;
           const uint32_t bar_a = (flags & kUCommitAcc0) ? b_acc0 : ((flags & kUCommitAcc1) ? b_acc1 : 0u);
           if (ts)
@@ -700,7 +751,35 @@ field_x3_kernel(const __grid_constant__ TcProgram prog, const __grid_constant__ 
         const TcStep& st = prog.steps[si];
         const float4* bias4 = cst.b4 + si * 64;        // this step's 256 biases
         const float inv_s = cst.inv_scale[si];          // undoes the step's power-of-two weight scale
-        if (st.epi == kEpiHidden) {
+        if (st.epi == kEpiHidden && st.n_chunks == 1) {
+          // ---- 128-wide layer, one N = 128 chunk: every MMA of the layer is complete, so the
+          //      output overwrites the input in place; two 64-column instalments (x_ready[0] /
+          //      x_ready[2]) so that the next layer's first K-block starts under the second ----
+          const bool relu = st.relu != 0;
+          uint32_t ph[16], pl[16];
+          float va[32], vb[32];
+          const int ca = hs * 32, cb2 = 64 + hs * 32;
+          mbar_wait(&bars->acc_ready[0], n_acc0++ & 1, dead);
+          tc_fence_after();
+          tr.ev(si, 0);
+          x3_ld32(t_lane + ca, va);
+          x3_ld32(t_lane + cb2, vb);
+          tmem_ld_wait();
+          tc_fence_before();
+          mbar_arrive(&bars->x_ready[1]);               // the accumulator may be overwritten
+          x3_piece(va, bias4 + (ca >> 2), inv_s, relu, false, cst.alpha4, row.alpha, ph, pl);
+          tst_piece(t_lane, ca, ph, pl);
+          tmem_st_wait();
+          tc_fence_before();
+          mbar_arrive(&bars->x_ready[0]);
+          tr.ev(si, 3);
+          x3_piece(vb, bias4 + (cb2 >> 2), inv_s, relu, false, cst.alpha4, row.alpha, ph, pl);
+          tst_piece(t_lane, cb2, ph, pl);
+          tmem_st_wait();
+          tc_fence_before();
+          mbar_arrive(&bars->x_ready[2]);
+          tr.ev(si, 5);
+        } else if (st.epi == kEpiHidden) {
           const int cols = st.chunk_n >> 1;            // columns of a chunk handled by this thread: 64 or 32
           const bool wide = cols == 64;
           const bool relu = st.relu != 0, adot = st.alpha_dot != 0;

@@ -58,6 +58,7 @@ constexpr int kScanOff = kPartOff + 512;                       // fused composit
 constexpr int kBarOff = kScanOff + 256;
 constexpr int kX3SmemBytes = kBarOff + 256;
 static_assert(kX3SmemBytes <= 232448, "shared memory");
+static_assert(kX3Slots % 2 == 0, "slots are released in pairs");
 // TMEM columns
 constexpr uint32_t kTmCols = 512, kTmAHi = 256, kTmALo = 384;
 // Unit table (TcUnit::a0_lo / a1_lo, built by build_tc_program): bit 31 set = the A
@@ -67,7 +68,7 @@ constexpr uint32_t kUnitATmem = 0x80000000u;
 
 struct X3Bars {
   uint64_t full[kX3Slots];
-  uint64_t empty[kX3Slots];
+  uint64_t empty[kX3Slots / 2];  // one per PAIR of slots: released by one commit after the pair's second unit
   uint64_t acc_ready[2];
   uint64_t x_free;
   uint64_t x_ready[3];           // [0] chunk-0 epilogue done | [1] chunk-1 accumulator read | [2] chunk-1 epilogue done
@@ -166,9 +167,6 @@ __device__ __forceinline__ void posenc_block_x3(uint8_t* bh, uint8_t* bl, int r,
     sincos_f64((double)x[c], sn[c], cs[c]);
     a32[c] = x[c];
   }
-  const double kHp = (double)kHalfPiF;                       // fl32(pi/2) = pi/2 + 4.371e-8
-  const double kCh = -4.37113900018624124e-08;               // cos(fl32(pi/2))
-  const double kSh = 9.99999999999999001e-01;                // sin(fl32(pi/2))
 #pragma unroll
   for (int f = 0; f < 10; ++f) {
     if (f < F) {
@@ -181,11 +179,11 @@ __device__ __forceinline__ void posenc_block_x3(uint8_t* bh, uint8_t* bl, int r,
           feat[ks - 32 * kHS] = window ? w * v : v;
         }
         if (kc >= 32 * kHS && kc < 32 * kHS + 32) {
-          const float t = a32[c] + kHalfPiF;                 // the reference's fp32 argument
-          const double e = (double)t - ((double)a32[c] + kHp);
-          const double S = fma(sn[c], kCh, cs[c] * kSh), C = fma(cs[c], kCh, -sn[c] * kSh);
-          const double e2 = e * e;
-          const double v64 = fma(S, -0.5 * e2, S) + C * fma(e2 * e, -1.0 / 6.0, e);
+          // the reference's fp32 argument t = fl32(a + fl32(pi/2)) = a + pi/2 + eps (|eps| <= ulp(t)/2 +
+          // 4.4e-8 <= 4e-5): sin t = cos(a + eps) = cs (1 - eps^2/2) - sn eps  (the eps^3 term is < 1e-14)
+          const float t = a32[c] + kHalfPiF;
+          const double eps = ((double)t - (double)a32[c]) - 1.57079632679489661923;
+          const double v64 = fma(-sn[c], eps, fma(cs[c], -0.5 * eps * eps, cs[c]));
           const float v = (float)v64;
           feat[kc - 32 * kHS] = window ? w * v : v;
         }
@@ -357,10 +355,14 @@ __device__ __forceinline__ void issue_x3_head(uint32_t d, uint64_t a_hi, uint64_
 //   accumulator commits.  Returns the probe bits: 1 = the next unit's weight slot has
 //   landed, 2/4/8 = x_ready[0/1/2].
 #define NFB_X3_TAIL_PROLOGUE \
-      ".reg .pred pt, pw, px0, px1, px2, pd0, pd1, pd2, pcx, pca, pmc;\n\t" \
+      ".reg .pred pt, pw, px0, px1, px2, pd0, pd1, pd2, pcx, pca, pmc, pe, pe1, pe2;\n\t" \
       ".reg .b32 t0, t1, t2;\n\t" \
       "setp.eq.b32 pt, 0, 0;\n\t" \
       "setp.ne.b32 pmc, %17, 0;\n\t" \
+      "setp.ne.b32 pe, %7, 0;\n\t" \
+      "and.pred pe2, pe, pmc;\n\t" \
+      "not.pred pe1, pmc;\n\t" \
+      "and.pred pe1, pe1, pe;\n\t" \
       "setp.ne.b32 pd0, %12, 0;\n\t" \
       "setp.ne.b32 pd1, %13, 0;\n\t" \
       "setp.ne.b32 pd2, %14, 0;\n\t" \
@@ -377,9 +379,10 @@ __device__ __forceinline__ void issue_x3_head(uint32_t d, uint64_t a_hi, uint64_
       "@pd1 mbarrier.test_wait.parity.shared::cta.b64 px1, [%13], %15;\n\t" \
       "@pd2 mbarrier.test_wait.parity.shared::cta.b64 px2, [%14], %15;\n\t"
 #define NFB_X3_TAIL_EPILOGUE \
-      "@!pmc tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%7];\n\t" \
+      /* slot release: every second unit (a PAIR of slots per commit: a commit costs ~120 cycles of issue) */ \
+      "@pe1 tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%7];\n\t" \
       /* CTA-pair build: the weight slot is shared (multicast copies): release it in both CTAs */ \
-      "@pmc tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%7], %16;\n\t" \
+      "@pe2 tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%7], %16;\n\t" \
       "@pcx tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%8];\n\t" \
       "@pca tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%9];\n\t" \
       "selp.u32 %0, 1, 0, pw;\n\t" \
@@ -529,7 +532,8 @@ field_x3_kernel(const __grid_constant__ TcProgram prog, const __grid_constant__ 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == kMmaWarp * 32) {
     for (int i = 0; i < kX3Slots; ++i) {
-      mbar_init(&bars->full[i], 1); mbar_init(&bars->empty[i], kPair ? 2 : 1);
+      mbar_init(&bars->full[i], 1);
+      if ((i & 1) == 0) mbar_init(&bars->empty[i >> 1], kPair ? 2 : 1);
     }
     mbar_init(&bars->acc_ready[0], 1); mbar_init(&bars->acc_ready[1], 1);
     mbar_init(&bars->x_free, 1);
@@ -583,7 +587,7 @@ field_x3_kernel(const __grid_constant__ TcProgram prog, const __grid_constant__ 
         for (int u = 0; u < n; ++u) {
           uint8_t* dst = stages + sg * kX3SlotBytes;
           const uint8_t* from = src + (size_t)u * bytes;
-          mbar_wait(&bars->empty[sg], ph ^ 1, dead);
+          if ((sg & 1) == 0) mbar_wait(&bars->empty[sg >> 1], ph ^ 1, dead);
           tr.ev(si, u);
 #ifdef NFB_X3_EXP_NOFILL
           // timing experiment (garbage results): only the first pass over the ring is copied
@@ -655,7 +659,7 @@ field_x3_kernel(const __grid_constant__ TcProgram prog, const __grid_constant__ 
           const uint32_t nxr = xr + ((flags & kUStepEnd) ? 1u : 0u);
           const uint32_t px0 = (c1.z & 2) ? b_x0 : 0u, px1 = (c1.z & 4) ? b_x1 : 0u;
           const uint32_t px2 = (c1.z & 8) ? b_x2 : 0u;
-          const uint32_t d_cur = d0, idesc = c0.w, bar_e = b_empty + sg * 8;
+          const uint32_t d_cur = d0, idesc = c0.w, bar_e = (sg & 1) ? b_empty + (sg >> 1) * 8 : 0u;
           const uint64_t bd_cur = bd, a_hi = ad0;
           d0 = tmem_base + n0.z;
           bd = desc_hi | (uint64_t)(st_lo + nsg * (kX3SlotBytes >> 4));
@@ -995,7 +999,10 @@ inline int run_field_x3(nfb_handle* h, int level, const FieldArgs& a, cudaStream
   if (fuse && (a.samples_per_ray % kTileRows != 0 || a.num_rows % a.samples_per_ray != 0))
     return fail("fused composite needs samples_per_ray to be a multiple of %d", kTileRows);
   const long long groups = fuse ? a.num_rows / a.samples_per_ray : tiles;
-#ifdef NFB_X3_EXP_NOPAIR
+  // The CTA-pair launch (two CTAs share one multicast weight stream: half the L2 reads) measured 1 % SLOWER
+  // than independent CTAs once the ring was deep enough (L2 throughput is at 12 %; the coupling of the two
+  // issuers through the shared slot release costs more): off unless built with -DNFB_X3_PAIR.
+#ifndef NFB_X3_PAIR
   h->x3_pair_ok = 0;
 #endif
   if (groups >= (long long)h->sm_count && h->x3_pair_ok != 0) {

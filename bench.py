@@ -65,6 +65,11 @@ WORKLOADS = {
         desc='training.train_step on the gpu_quarterhd.gin batch: {B} rays per GPU x (128+128) samples (global '
              'batch 6144 split over the ranks as the reference does): value_and_grad of the photometric loss '
              '(fp32, layer-wise tape), ONE NCCL all_reduce of the flat gradient, Adam'),
+    'vrig-trainstep': dict(
+        rays=6144, nc=128, nf=128, fp=8, fw=6, app=False, cam=True, flop=1364480, trainstep=True, reg=True,
+        desc='training.train_step as gpu_vrig_paper.gin configures it: {B} rays per GPU x (128+128) samples, '
+             "elastic loss on the warp Jacobian of every coarse sample (elastic_reduce_method='weight', log_svals), "
+             'background loss on {B} points, photometric loss; ONE NCCL all_reduce of the flat gradient, Adam'),
     'fullhd-65536': dict(
         rays=65536, nc=256, nf=256, fp=10, fw=8, app=True, cam=False, flop=1382400,
         desc='gpu_fullhd.gin model dims at {B} rays x (256+256) samples'),
@@ -617,6 +622,13 @@ def measure_train_step(args, wl, ctx):
            'rgb': torch.rand(B, 3, generator=g).to(dev)}
   sp = training.ScalarParams(learning_rate=1e-3)
   chunk = 1024
+  kw = {}
+  if wl.get('reg'):
+    # gpu_vrig_paper.gin:31,52-61
+    sp = training.ScalarParams(learning_rate=1e-3, elastic_loss_weight=0.001, background_loss_weight=1.0)
+    batch['background_points'] = (torch.rand(B, 3, generator=g) * 0.6 - 0.3).to(dev)
+    kw = dict(use_elastic_loss=True, elastic_reduce_method='weight', use_background_loss=True)
+    chunk = 512
 
   def barrier():
     if world > 1:
@@ -625,7 +637,7 @@ def measure_train_step(args, wl, ctx):
 
   losses = []
   for _ in range(max(1, min(args.warmup, 2))):
-    state, stats, _ = training.train_step(model, 0, state, batch, sp, chunk_rays=chunk)
+    state, stats, _ = training.train_step(model, 0, state, batch, sp, chunk_rays=chunk, **kw)
   barrier()
   sampler = ClockSampler(ctx['local_rank'])
   sampler.start()
@@ -634,7 +646,7 @@ def measure_train_step(args, wl, ctx):
   barrier()
   for _ in range(args.steps):
     t = {}
-    state, stats, _ = training.train_step(model, 0, state, batch, sp, chunk_rays=chunk, timings=t)
+    state, stats, _ = training.train_step(model, 0, state, batch, sp, chunk_rays=chunk, timings=t, **kw)
     tms.append(t)
     losses.append(float(stats['fine']['loss/total']))
   barrier()
@@ -654,7 +666,7 @@ def measure_train_step(args, wl, ctx):
       'unit': 'ray-samples/s', 'n_gpus': world, 'steps': args.steps, 'warmup': max(1, min(args.warmup, 2)),
       'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,
       'dtype': 'fp32 (training tier: layer-wise SIMT GEMMs, forward + backward)', 'data': 'synthetic',
-      'config': {'workload': workload_text(wl, B), 'workload_name': 'quarterhd-trainstep',
+      'config': {'workload': workload_text(wl, B), 'workload_name': args.workload,
                  'rays_per_gpu': B, 'global_batch': B * world, 'precision': 'fp32',
                  'parallelism': f'data parallel x{world}: one NCCL all_reduce of the flat gradient '
                                 f'({n_params} fp32 = {n_params * 4 / 1e6:.1f} MB) per step',
@@ -663,6 +675,7 @@ def measure_train_step(args, wl, ctx):
       'adam_ms': float(tot[3]) / args.steps, 'train_flop_per_step': 3 * world * B * evals * wl['flop'],
       'achieved_tflops_fp32': 3 * world * B * evals * wl['flop'] / (ms * 1e-3) / 1e12 / world,
       'loss_first_last': [losses[0], losses[-1]], 'clocks': clocks, 'gpu_launches': int(launches),
+      'stats_last_step': {lv: {k: float(v) for k, v in stats[lv].items()} for lv in ('coarse', 'fine')},
   }
 
 

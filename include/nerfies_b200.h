@@ -300,6 +300,15 @@ int nfb_set_trace(nfb_handle* h, long long* buffer, int capacity);
  * launches afterwards.  No reference analogue. */
 int nfb_debug_provoke_timeout(nfb_handle* h, int enabled);
 
+/* The asynchronous entry points (nfb_render_forward, nfb_render_samples, nfb_warp_forward, ...) return
+ * before their kernels finish, so a tensor-core kernel's protocol time-out (see the conventions above)
+ * is only seen by a LATER call.  nfb_check_abort reports it for the work already submitted: with
+ * synchronize != 0 it first waits for `stream`; returns 0 or < 0 (nfb_last_error).  nfb_reset_abort
+ * waits for the device and clears the process-wide flag, after which launches are accepted again.
+ * No reference analogue. */
+int nfb_check_abort(void* stream, int synchronize);
+int nfb_reset_abort(void);
+
 /* Hardware self-test of the tcgen05 building blocks (UMMA descriptors, 128-byte
  * swizzle, TMEM, bulk-copy ring): C[128,N] = bf16(A[128,K]) x bf16(W[K,N]), fp32
  * accumulate.  K <= 320, N <= 256; device pointers. */

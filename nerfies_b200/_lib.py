@@ -19,7 +19,7 @@ SYMBOLS = [
     'nfb_set_profiling', 'nfb_field_time_ms', 'nfb_selftest_gemm', 'nfb_set_trace', 'nfb_selftest_microbench',
     'nfb_camera_rays', 'nfb_pixels_to_rays', 'nfb_selftest_gemm2', 'nfb_selftest_gemm3',
     'nfb_debug_provoke_timeout', 'nfb_set_time_alpha', 'nfb_train_value_and_grad', 'nfb_adam_step',
-    'nfb_train_value_and_grad_reg', 'nfb_warp_jacobian',
+    'nfb_train_value_and_grad_reg', 'nfb_warp_jacobian', 'nfb_check_abort', 'nfb_reset_abort',
 ]
 
 class TrainReg(ctypes.Structure):
@@ -160,6 +160,10 @@ def load():
   lib.nfb_train_value_and_grad_reg.restype = ci
   lib.nfb_warp_jacobian.argtypes = [vp, ci, vp, vp, cf, vp, vp, vp]
   lib.nfb_warp_jacobian.restype = ci
+  lib.nfb_check_abort.argtypes = [vp, ci]
+  lib.nfb_check_abort.restype = ci
+  lib.nfb_reset_abort.argtypes = []
+  lib.nfb_reset_abort.restype = ci
   lib.nfb_adam_step.argtypes = [vp, vp, vp, vp, ctypes.c_longlong, cf, cf, cf, cf, ctypes.c_longlong, vp]
   lib.nfb_adam_step.restype = ci
   lib.nfb_set_time_alpha.argtypes = [vp, cf]

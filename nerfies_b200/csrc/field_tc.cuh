@@ -988,8 +988,12 @@ inline int build_tc_program(nfb_handle* h, int level, long long* wbytes, long lo
         if (t.n_chunks == 2 && i == first_of_chunk[1]) u.flags |= kUWaitX1;
         if (t.n_chunks == 1 && i == 0) u.flags |= kUWaitX1;
         if (i == first_late) u.flags |= kUWaitX2;
-        if (t.n_chunks == 2 && i == (last_low >= 0 ? last_low : 0)) u.flags |= kUCommitXFree;
+        // "the blocks chunk 0's epilogue overwrites are no longer read": a separate commit only when one of
+        // their readers is issued after chunk 0's last unit - otherwise acc_ready[0] already implies it
+        // (a commit covers every MMA issued before it) and the step is marked kb_free = -2: no x_free.
+        if (t.n_chunks == 2 && last_low > last_of_chunk[0] && i == last_low) u.flags |= kUCommitXFree;
       }
+      if (t.n_chunks == 2) tp.steps[si].kb_free = last_low > last_of_chunk[0] ? 0 : -2;
       tp.units[first].flags |= kUWaitX0;
       TcUnit& last = tp.units[tp.n_units - 1];
 

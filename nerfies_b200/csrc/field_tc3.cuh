@@ -808,7 +808,7 @@ field_x3_kernel(const __grid_constant__ TcProgram prog, const __grid_constant__ 
             x3_piece(va, bias4 + (col0 >> 2), inv_s, relu, adot, cst.alpha4 + (col0 >> 2), row.alpha, ph, pl);
           }
           tr.ev(si, 1);
-          mbar_wait(&bars->x_free, n_free++ & 1, dead);
+          if (st.kb_free != -2) mbar_wait(&bars->x_free, n_free++ & 1, dead);    // (-2: implied by acc_ready[0])
           tr.ev(si, 2);
           tst_piece(t_lane, col0, ph, pl);
           if (wide) tst_piece(t_lane, col0 + 32, ph + 16, pl + 16);

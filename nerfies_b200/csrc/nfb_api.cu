@@ -457,7 +457,7 @@ int ensure_abort_flag() {
 int abort_check() {
   if (g_abort_host && *reinterpret_cast<volatile int*>(g_abort_host))
     return fail("a tcgen05 kernel aborted: an mbarrier wait timed out (protocol error); its results are invalid "
-                "and this process cannot run further tensor-core launches");
+                "and tensor-core launches are refused until nfb_reset_abort()");
   return 0;
 }
 
@@ -571,6 +571,18 @@ float nfb_field_time_ms(nfb_handle* h, int level) {
   float ms = -1.f;
   if (cudaEventElapsedTime(&ms, h->ev[level][0], h->ev[level][1]) != cudaSuccess) { fail("cudaEventElapsedTime failed"); return -1.f; }
   return ms;
+}
+
+int nfb_check_abort(void* stream, int synchronize) {
+  if (synchronize) NFB_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  return abort_check();
+}
+
+int nfb_reset_abort(void) {
+  // only meaningful once every stream that ran a tensor-core launch has drained
+  NFB_CUDA(cudaDeviceSynchronize());
+  if (g_abort_host) *reinterpret_cast<volatile int*>(g_abort_host) = 0;
+  return 0;
 }
 
 int nfb_selftest_gemm(int K, int N, const float* A, const float* W, float* C, void* stream) {

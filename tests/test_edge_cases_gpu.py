@@ -164,12 +164,22 @@ def test_protocol_error_aborts_instead_of_hanging():
         print('NO-ERROR')
       except Exception as e:
         print('ERROR:', e)
+      # the asynchronous call itself returned 0: nfb_check_abort reports the failure of submitted work,
+      # nfb_reset_abort re-arms the process
+      print('CHECK', hd.lib.nfb_check_abort(None, 1))
+      hd.lib.nfb_debug_provoke_timeout(hd.h, 0)
+      print('RESET', hd.lib.nfb_reset_abort(), hd.lib.nfb_check_abort(None, 1))
+      out = model.apply({'params': params}, rays, warp_extra={'alpha': 8.0})
+      torch.cuda.synchronize()
+      print('RECOVERED', bool(torch.isfinite(out['fine']['rgb']).all()))
   ''')
   env = dict(os.environ)
   root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
   out = subprocess.run([sys.executable, '-c', code], cwd=root, env=env, capture_output=True, text=True,
                        timeout=120)
   assert 'ERROR:' in out.stdout and 'mbarrier wait timed out' in out.stdout, (out.stdout, out.stderr[-2000:])
+  assert 'CHECK -1' in out.stdout and 'RESET 0 0' in out.stdout and 'RECOVERED True' in out.stdout, (
+      out.stdout, out.stderr[-2000:])
 
 
 def test_cta_pair_variant_is_bit_identical(monkeypatch):

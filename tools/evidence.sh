@@ -1,12 +1,17 @@
 # Round evidence set (run on the GPU box): default bench line (fp16x3 headline + bf16 + eval frame
-# + CPU baseline), the other BASELINE workloads, ncu launch list of one step, ncu --set full
-# captures of the two tensor-core field kernels and of the camera kernel, block-0 timelines.
+# + CPU baseline), the other BASELINE workloads, the train_step workloads, ncu launch list of one
+# step, ncu --set full captures of the two tensor-core field kernels and of the camera kernel,
+# block-0 timeline.  Every command reads /dev/null (nothing may wait on stdin on the box).
 set -x
 R=r02
+exec </dev/null
 python bench.py --steps 10 --warmup 3 > gpurun_out/${R}_bench_default_1gpu.json 2> gpurun_out/${R}_bench_default_1gpu.err
 tail -c 600 gpurun_out/${R}_bench_default_1gpu.json
 for w in quarterhd-train vrig-train fullhd-train; do
   python bench.py --workload $w --steps 5 --no-cpu-baseline > gpurun_out/${R}_bench_$w.json 2> gpurun_out/${R}_bench_$w.err
+done
+for w in quarterhd-trainstep vrig-trainstep; do
+  timeout 300 python bench.py --workload $w --steps 3 --warmup 1 > gpurun_out/${R}_bench_$w.json 2> gpurun_out/${R}_bench_$w.err
 done
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${R}_launches_fp16x3_ncu.csv python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-also --no-parity > gpurun_out/ncu_list.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:field_x3 -s 3 -c 1 -f -o gpurun_out/${R}_prof_x3 python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-also --no-parity > gpurun_out/ncu_x3.log 2>&1
@@ -14,6 +19,7 @@ tail -2 gpurun_out/ncu_x3.log | cut -c1-200
 ncu --set full --clock-control none --import-source on -k regex:field_tc -s 3 -c 1 -f -o gpurun_out/${R}_prof_tc python bench.py --precision bf16 --steps 1 --warmup 1 --no-cpu-baseline --no-also --no-parity > gpurun_out/ncu_tc.log 2>&1
 ncu --set full --clock-control none -k regex:camera_rays -s 6 -c 2 -f -o gpurun_out/${R}_prof_camera python tools/bench_camera.py > gpurun_out/ncu_cam.log 2>&1
 python tools/bench_camera.py > gpurun_out/${R}_bench_camera.json 2>/dev/null
+python tools/microbench_tmem_a.py > gpurun_out/${R}_microbench_tmem_a.json 2>/dev/null
 python tools/build_variant.py trace -DNFB_TRACE >/dev/null 2>&1 || true
 PREC=fp16x3 STEP_LO=0 STEP_HI=40 timeout 200 python tools/trace_tc.py > gpurun_out/${R}_x3_timeline.txt 2>&1
 head -24 gpurun_out/${R}_x3_timeline.txt

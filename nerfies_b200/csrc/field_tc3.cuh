@@ -65,6 +65,18 @@ constexpr uint32_t kTmCols = 512, kTmAHi = 256, kTmALo = 384;
 // K-block is in TMEM and bits 0..15 are its column offset; otherwise the value is the
 // shared-memory byte offset >> 4 of the input block image.
 constexpr uint32_t kUnitATmem = 0x80000000u;
+// x_ready arrivals.  NFB_X3_WARP_ARRIVE (A/B build): one arrival per epilogue WARP (bar.warp.sync, then
+// lane 0) instead of one per thread - 8 instead of 256 serialised updates of the same barrier word.
+#ifdef NFB_X3_WARP_ARRIVE
+constexpr int kXrCount = kX3EpiThreads / 32;
+__device__ __forceinline__ void xr_arrive(uint64_t* bar) {
+  __syncwarp();
+  if ((threadIdx.x & 31) == 0) mbar_arrive(bar);
+}
+#else
+constexpr int kXrCount = kX3EpiThreads;
+__device__ __forceinline__ void xr_arrive(uint64_t* bar) { mbar_arrive(bar); }
+#endif
 
 struct X3Bars {
   uint64_t full[kX3Slots];
@@ -537,7 +549,7 @@ field_x3_kernel(const __grid_constant__ TcProgram prog, const __grid_constant__ 
     }
     mbar_init(&bars->acc_ready[0], 1); mbar_init(&bars->acc_ready[1], 1);
     mbar_init(&bars->x_free, 1);
-    for (int k = 0; k < 3; ++k) mbar_init(&bars->x_ready[k], kX3EpiThreads);
+    for (int k = 0; k < 3; ++k) mbar_init(&bars->x_ready[k], kXrCount);
     fence_barrier_init();
   }
   if (warp == kMmaWarp) tmem_alloc(&bars->tmem_slot, kTmCols);
@@ -700,9 +712,14 @@ field_x3_kernel(const __grid_constant__ TcProgram prog, const __grid_constant__ 
     auto arrive_all = [&]() {
       fence_proxy_async();
       tc_fence_before();
-      mbar_arrive(&bars->x_ready[0]);
-      mbar_arrive(&bars->x_ready[1]);
-      mbar_arrive(&bars->x_ready[2]);
+#ifdef NFB_X3_WARP_ARRIVE
+      __syncwarp();
+      if (lane == 0) { mbar_arrive(&bars->x_ready[0]); mbar_arrive(&bars->x_ready[1]); mbar_arrive(&bars->x_ready[2]); }
+#else
+      xr_arrive(&bars->x_ready[0]);
+      xr_arrive(&bars->x_ready[1]);
+      xr_arrive(&bars->x_ready[2]);
+#endif
     };
     // Sample point of this thread's row in tile `tile`, and the first input block
     // (model_utils.py:72-73; warping.py:325-326 / models.py:270).
@@ -770,18 +787,18 @@ field_x3_kernel(const __grid_constant__ TcProgram prog, const __grid_constant__ 
           x3_ld32(t_lane + cb2, vb);
           tmem_ld_wait();
           tc_fence_before();
-          mbar_arrive(&bars->x_ready[1]);               // the accumulator may be overwritten
+          xr_arrive(&bars->x_ready[1]);               // the accumulator may be overwritten
           x3_piece(va, bias4 + (ca >> 2), inv_s, relu, false, cst.alpha4, row.alpha, ph, pl);
           tst_piece(t_lane, ca, ph, pl);
           tmem_st_wait();
           tc_fence_before();
-          mbar_arrive(&bars->x_ready[0]);
+          xr_arrive(&bars->x_ready[0]);
           tr.ev(si, 3);
           x3_piece(vb, bias4 + (cb2 >> 2), inv_s, relu, false, cst.alpha4, row.alpha, ph, pl);
           tst_piece(t_lane, cb2, ph, pl);
           tmem_st_wait();
           tc_fence_before();
-          mbar_arrive(&bars->x_ready[2]);
+          xr_arrive(&bars->x_ready[2]);
           tr.ev(si, 5);
         } else if (st.epi == kEpiHidden) {
           const int cols = st.chunk_n >> 1;            // columns of a chunk handled by this thread: 64 or 32
@@ -819,7 +836,7 @@ field_x3_kernel(const __grid_constant__ TcProgram prog, const __grid_constant__ 
           tmem_st_wait();                               // the TMEM stores have completed ...
           if (st.write_cond) fence_proxy_async();       // ... and the input-block stores are visible to the MMAs
           tc_fence_before();
-          mbar_arrive(&bars->x_ready[0]);
+          xr_arrive(&bars->x_ready[0]);
           tr.ev(si, 3);
           // ---- chunk 1: every MMA of the layer is complete, store directly ----
           const int col1 = st.chunk_n + col0;
@@ -832,7 +849,7 @@ field_x3_kernel(const __grid_constant__ TcProgram prog, const __grid_constant__ 
             x3_ld32(t_lane + col1 + 32, vb);
             tmem_ld_wait();
             tc_fence_before();
-            mbar_arrive(&bars->x_ready[1]);             // this accumulator may be overwritten (next step's chunk 1)
+            xr_arrive(&bars->x_ready[1]);             // this accumulator may be overwritten (next step's chunk 1)
             x3_piece(va, bias4 + (col1 >> 2), inv_s, relu, adot, cst.alpha4 + (col1 >> 2), row.alpha, ph, pl);
             tst_piece(t_lane, col1, ph, pl);
             x3_piece(vb, bias4 + (col1 >> 2) + 8, inv_s, relu, adot, cst.alpha4 + (col1 >> 2) + 8, row.alpha, ph, pl);
@@ -842,14 +859,14 @@ field_x3_kernel(const __grid_constant__ TcProgram prog, const __grid_constant__ 
             x3_ld32(t_lane + col1, va);
             tmem_ld_wait();
             tc_fence_before();
-            mbar_arrive(&bars->x_ready[1]);
+            xr_arrive(&bars->x_ready[1]);
             x3_piece(va, bias4 + (col1 >> 2), inv_s, relu, adot, cst.alpha4 + (col1 >> 2), row.alpha, ph, pl);
             tst_piece(t_lane, col1, ph, pl);
           }
           if (adot && hs == 1) alpha_part[r] = row.alpha;   // read by the row's first thread at the rgb step
           tmem_st_wait();
           tc_fence_before();
-          mbar_arrive(&bars->x_ready[2]);
+          xr_arrive(&bars->x_ready[2]);
           tr.ev(si, 5);
         } else {
           // ---- heads: N = 16 accumulator columns, one chunk (both threads of a row

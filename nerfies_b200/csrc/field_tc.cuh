@@ -826,12 +826,33 @@ inline int x3_unit_order(const TcProgram& tp, int si, int* oc, int* okb) {
   int split = 99;
   if (si > 0 && !after_heads) split = x3_split_of(tp.steps[si - 1]);
   int n = 0;
+  int lst[2][2][8], cnt[2][2] = {{0, 0}, {0, 0}};     // [phase][chunk] -> K-blocks
   for (int phase = 0; phase < 2; ++phase)
     for (int c = 0; c < t.n_chunks; ++c)
       for (int kb = 0; kb < t.nkb; ++kb) {
         const bool late = t.src[kb] < kSrcIn && t.src[kb] >= split;
-        if ((int)late == phase) { oc[n] = c; okb[n] = kb; ++n; }
+        if ((int)late == phase) lst[phase][c][cnt[phase][c]++] = kb;
       }
+  auto put = [&](int c, int kb) { oc[n] = c; okb[n] = kb; ++n; };
+#ifndef NFB_X3_ORDER_OLD
+  if (t.n_chunks == 2 && cnt[1][0] > 0 && cnt[0][1] > 0) {
+    // Balanced order: A(c0), A(c1) but its last unit, B(c0), last of A(c1), B(c1).  The chunk-0
+    // accumulator completes |B| + 1 units before the end of the step (its epilogue - accumulator
+    // read, split, wait for the last reader of the blocks it overwrites, store - then has about one
+    // unit of slack before the next step's first MMA needs it), and the first phase-B unit still
+    // comes |A(c0)| + |A(c1)| - 1 units after the start of the step (the previous chunk-1 epilogue
+    // has that long).  With A, A, B, B both hand-offs were on the edge: ~2 units for a ~1.8 K-cycle chain.
+    for (int i = 0; i < cnt[0][0]; ++i) put(0, lst[0][0][i]);
+    for (int i = 0; i + 1 < cnt[0][1]; ++i) put(1, lst[0][1][i]);
+    for (int i = 0; i < cnt[1][0]; ++i) put(0, lst[1][0][i]);
+    put(1, lst[0][1][cnt[0][1] - 1]);
+    for (int i = 0; i < cnt[1][1]; ++i) put(1, lst[1][1][i]);
+    return n;
+  }
+#endif
+  for (int phase = 0; phase < 2; ++phase)
+    for (int c = 0; c < t.n_chunks; ++c)
+      for (int i = 0; i < cnt[phase][c]; ++i) put(c, lst[phase][c][i]);
   return n;
 }
 

@@ -164,10 +164,13 @@ __device__ __forceinline__ void sincos_f64(double x, double& s, double& c) {
 }
 
 // kHS: which 32-column half of the 64-column input block this thread writes.
+// posenc_pack_x3 leaves the 32 columns as packed fp16 hi / lo pairs in registers (4 x 16-byte chunks
+// per image): the next tile's encoding is computed while the input block is still being read and
+// stored later (store_packed_x3).
 template <int kHS>
-__device__ __forceinline__ void posenc_block_x3(uint8_t* bh, uint8_t* bl, int r, const float* x, int F,
-                                                const float* __restrict__ window,
-                                                const float* __restrict__ extra, int n_extra) {
+__device__ __forceinline__ void posenc_pack_x3(uint4* qh, uint4* ql, const float* x, int F,
+                                               const float* __restrict__ window,
+                                               const float* __restrict__ extra, int n_extra) {
   float feat[32];
 #pragma unroll
   for (int j = 0; j < 32; ++j) feat[j] = 0.f;
@@ -213,7 +216,29 @@ __device__ __forceinline__ void posenc_block_x3(uint8_t* bh, uint8_t* bl, int r,
     if (k >= d && k < d + n_extra) feat[j] = __ldg(extra + (k - d));
   }
 #pragma unroll
-  for (int c = 0; c < 4; ++c) store_chunk_x3(bh, bl, r, 4 * kHS + c, feat + 8 * c);
+  for (int c = 0; c < 4; ++c) {
+    const float* v = feat + 8 * c;
+    split_pair(v[0], v[1], qh[c].x, ql[c].x);
+    split_pair(v[2], v[3], qh[c].y, ql[c].y);
+    split_pair(v[4], v[5], qh[c].z, ql[c].z);
+    split_pair(v[6], v[7], qh[c].w, ql[c].w);
+  }
+}
+__device__ __forceinline__ void store_packed_x3(uint8_t* bh, uint8_t* bl, int r, int hs, const uint4* qh, const uint4* ql) {
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const uint32_t off = swz_off(r, 4 * hs + c);
+    *reinterpret_cast<uint4*>(bh + off) = qh[c];
+    *reinterpret_cast<uint4*>(bl + off) = ql[c];
+  }
+}
+template <int kHS>
+__device__ __forceinline__ void posenc_block_x3(uint8_t* bh, uint8_t* bl, int r, const float* x, int F,
+                                                const float* __restrict__ window,
+                                                const float* __restrict__ extra, int n_extra) {
+  uint4 qh[4], ql[4];
+  posenc_pack_x3<kHS>(qh, ql, x, F, window, extra, n_extra);
+  store_packed_x3(bh, bl, r, kHS, qh, ql);
 }
 
 __device__ __forceinline__ void cond_to_block_x3(uint8_t* bh, uint8_t* bl, int r, const float* __restrict__ cond,
@@ -245,17 +270,19 @@ __device__ __forceinline__ void cond_to_block_x3(uint8_t* bh, uint8_t* bl, int r
 // error: an absolute 2^-25, far below the fp32 noise of a layer output.  Saturating
 // conversions: |v| > 65504 does not become inf.
 template <bool kRelu>
-__device__ __forceinline__ void x3_piece_fast(const float* v, const float4* __restrict__ bq4, float inv_s,
+__device__ __forceinline__ void x3_piece_fast(float* v, const float4* __restrict__ bq4, float inv_s,
                                               uint32_t* hi16, uint32_t* lo16) {
   const uint64_t is2 = pack_f32x2(inv_s, inv_s);
 #pragma unroll
   for (int j = 0; j < 32; j += 4) {
-    const float4 bq = bq4[j >> 2];                  // constant bank, warp-uniform address
+    const float4 bq = bq4[j >> 2];                  // preloaded registers (bias_preload)
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       uint64_t r, t, d;
       asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(pack_f32x2(v[j + 2 * h], v[j + 2 * h + 1])), "l"(is2),
           "l"(h == 0 ? pack_f32x2(bq.x, bq.y) : pack_f32x2(bq.z, bq.w)));
+      // the pre-activation values stay in v[] (register renaming only; dead unless the alpha head reads them)
+      asm("mov.b64 {%0, %1}, %2;" : "=f"(v[j + 2 * h]), "=f"(v[j + 2 * h + 1]) : "l"(r));
       asm("and.b64 %0, %1, 0xFFFFE000FFFFE000;" : "=l"(t) : "l"(r));
       asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(r), "l"(t));
       float t0, t1, d0, d1;
@@ -271,38 +298,27 @@ __device__ __forceinline__ void x3_piece_fast(const float* v, const float4* __re
     }
   }
 }
-// The layer that also feeds the alpha head (one per level) needs the activated fp32 values.
-__device__ __forceinline__ void x3_piece_adot(const float* v, const float4* __restrict__ bq4, float inv_s, bool relu,
-                                              const float4* __restrict__ aw4, float& alpha,
-                                              uint32_t* hi16, uint32_t* lo16) {
-  const uint64_t is2 = pack_f32x2(inv_s, inv_s);
+// The alpha head (Dense(1) on the trunk output, one layer per level): an fp32 FMA chain over the
+// activated values x3_piece left in v[], evaluated AFTER the layer's hand-off (the head's result is
+// not needed before the rgb step) in the order the fused form used (columns ascending).
+__device__ __forceinline__ void alpha_dot32(const float* v, const float4* __restrict__ aw4, bool relu, float& alpha) {
 #pragma unroll
   for (int j = 0; j < 32; j += 4) {
-    const float4 bq = bq4[j >> 2];
-    uint64_t r0, r1;
-    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r0) : "l"(pack_f32x2(v[j], v[j + 1])), "l"(is2), "l"(pack_f32x2(bq.x, bq.y)));
-    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r1) : "l"(pack_f32x2(v[j + 2], v[j + 3])), "l"(is2), "l"(pack_f32x2(bq.z, bq.w)));
-    float t0, t1, t2, t3;
-    asm("mov.b64 {%0, %1}, %2;" : "=f"(t0), "=f"(t1) : "l"(r0));
-    asm("mov.b64 {%0, %1}, %2;" : "=f"(t2), "=f"(t3) : "l"(r1));
-    if (relu) { t0 = fmaxf(t0, 0.f); t1 = fmaxf(t1, 0.f); t2 = fmaxf(t2, 0.f); t3 = fmaxf(t3, 0.f); }
     const float4 w = aw4[j >> 2];
+    float t0 = v[j], t1 = v[j + 1], t2 = v[j + 2], t3 = v[j + 3];
+    if (relu) { t0 = fmaxf(t0, 0.f); t1 = fmaxf(t1, 0.f); t2 = fmaxf(t2, 0.f); t3 = fmaxf(t3, 0.f); }
     alpha = fmaf(t0, w.x, alpha); alpha = fmaf(t1, w.y, alpha);
     alpha = fmaf(t2, w.z, alpha); alpha = fmaf(t3, w.w, alpha);
-    split_pair(t0, t1, hi16[j >> 1], lo16[j >> 1]);
-    split_pair(t2, t3, hi16[(j >> 1) + 1], lo16[(j >> 1) + 1]);
   }
 }
-__device__ __forceinline__ void x3_piece(const float* v, const float4* __restrict__ bq4, float inv_s, bool relu,
-                                         bool adot, const float4* __restrict__ aw4, float& alpha,
+__device__ __forceinline__ void x3_piece(float* v, const float4* __restrict__ bq4, float inv_s, bool relu,
                                          uint32_t* hi16, uint32_t* lo16) {
 #ifdef NFB_X3_EXP_NOEPI
 #pragma unroll
   for (int j = 0; j < 16; ++j) { hi16[j] = 0x3c003c00u; lo16[j] = 0u; }
   return;
 #endif
-  if (adot) x3_piece_adot(v, bq4, inv_s, relu, aw4, alpha, hi16, lo16);
-  else if (relu) x3_piece_fast<true>(v, bq4, inv_s, hi16, lo16);
+  if (relu) x3_piece_fast<true>(v, bq4, inv_s, hi16, lo16);
   else x3_piece_fast<false>(v, bq4, inv_s, hi16, lo16);
 }
 
@@ -488,6 +504,17 @@ __device__ __forceinline__ uint32_t issue_x3_tail(uint32_t d, uint64_t a_hi, uin
 #undef NFB_X3_TAIL_PROLOGUE
 #undef NFB_X3_TAIL_PROBES
 #undef NFB_X3_TAIL_EPILOGUE
+
+// The 32 biases of a piece, fetched from the constant bank BEFORE the wait for the accumulator (the
+// empty asm keeps the loads there: otherwise they are sunk to their uses and their latency lands
+// on the hand-off chain accumulator -> epilogue -> next layer's first MMA).
+__device__ __forceinline__ void bias_preload(const float4* __restrict__ src, float4* dst) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    dst[i] = src[i];
+    asm volatile("" ::"f"(dst[i].x), "f"(dst[i].y), "f"(dst[i].z), "f"(dst[i].w));
+  }
+}
 
 // One 32-column piece of a layer's output (16 packed pairs per image) -> this thread's TMEM lane.
 // (NFB_X3_EXP_*: timing experiments of developer builds, garbage results.)
@@ -723,55 +750,110 @@ field_x3_kernel(const __grid_constant__ TcProgram prog, const __grid_constant__ 
     };
     // Sample point of this thread's row in tile `tile`, and the first input block
     // (model_utils.py:72-73; warping.py:325-326 / models.py:270).
-    auto begin_tile = [&](int tile) {
+    // The global loads of a tile's rows (z, ray origin / direction), issued EARLY - before the wait
+    // for the previous tile's last accumulator - so that their L2 latency is off the serial section
+    // between two tiles.
+    struct TilePref { float z, zn, org[3], dir[3]; };
+    auto tile_prefetch = [&](int tile, TilePref& pf) {
       long long m = (long long)tile * kTileRows + r;
-      row.valid = m < args.num_rows;
-      if (!row.valid) m = args.num_rows - 1;
-      row.m = m;
-      row.ray = m / S;
-      const float z = args.z_vals ? __ldg(args.z_vals + m) : 0.f;
+      if (m >= args.num_rows) m = args.num_rows - 1;
+      const long long ray = m / S;
+      pf.z = args.z_vals ? __ldg(args.z_vals + m) : 0.f;
+      const bool last = m + 1 == (ray + 1) * S;
+      pf.zn = (fuse && !last && args.z_vals) ? __ldg(args.z_vals + m + 1) : 0.f;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        pf.dir[c] = __ldg(args.directions + ray * 3 + c);
+        pf.org[c] = __ldg(args.origins + ray * 3 + c);
+      }
+    };
+    // Row state of tile `tile` (model_utils.py:72-73) ...
+    auto tile_row = [&](int tile, const TilePref& pf, X3Row& rw) {
+      long long m = (long long)tile * kTileRows + r;
+      rw.valid = m < args.num_rows;
+      if (!rw.valid) m = args.num_rows - 1;
+      rw.m = m;
+      rw.ray = m / S;
+      const float z = pf.z;
       float dir[3];
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
-        dir[c] = __ldg(args.directions + row.ray * 3 + c);
-        row.x[c] = __ldg(args.origins + row.ray * 3 + c) + z * dir[c];
+        dir[c] = pf.dir[c];
+        rw.x[c] = pf.org[c] + z * dir[c];
       }
       if (fuse) {
         // dists of volumetric_rendering (model_utils.py:98-104)
-        row.z = z;
-        row.last = m + 1 == (row.ray + 1) * S;
+        rw.z = z;
+        rw.last = m + 1 == (rw.ray + 1) * S;
         const float dnorm = sqrtf(dir[0] * dir[0] + dir[1] * dir[1] + dir[2] * dir[2]);
-        const float d = row.last ? (args.sample_at_infinity ? 1e10f : 1e-19f) : (__ldg(args.z_vals + m + 1) - z);
-        row.dist = d * dnorm;
+        const float d = rw.last ? (args.sample_at_infinity ? 1e10f : 1e-19f) : (pf.zn - z);
+        rw.dist = d * dnorm;
       }
-      const float* cond = args.cond + row.ray * prog.cond_stride;
-      if (do_warp) {
-        if (hs == 0) posenc_block_x3<0>(inh, inl, r, row.x, prog.Fw, args.window, cond, prog.G);
-        else posenc_block_x3<1>(inh, inl, r, row.x, prog.Fw, args.window, cond, prog.G);
-      } else {
-        if (args.warped && row.valid && hs == 0) {
+      if (!do_warp && args.warped && rw.valid && hs == 0) {
 #pragma unroll
-          for (int c = 0; c < 3; ++c) args.warped[m * 3 + c] = row.x[c];
-        }
-        if (hs == 0) posenc_block_x3<0>(inh, inl, r, row.x, prog.Fp, nullptr, nullptr, 0);
-        else posenc_block_x3<1>(inh, inl, r, row.x, prog.Fp, nullptr, nullptr, 0);
+        for (int c = 0; c < 3; ++c) args.warped[m * 3 + c] = rw.x[c];
       }
-      row.alpha = hs == 0 ? cst.alpha_b : 0.f;
+      rw.alpha = hs == 0 ? cst.alpha_b : 0.f;
+    };
+    // ... and this thread's half of its first input block (warping.py:325-326 / models.py:270) as
+    // packed fp16 hi / lo pairs in registers.
+    auto tile_encode = [&](const X3Row& rw, uint4* qh, uint4* ql) {
+      const float* cond = args.cond + rw.ray * prog.cond_stride;
+      if (do_warp) {
+        if (hs == 0) posenc_pack_x3<0>(qh, ql, rw.x, prog.Fw, args.window, cond, prog.G);
+        else posenc_pack_x3<1>(qh, ql, rw.x, prog.Fw, args.window, cond, prog.G);
+      } else {
+        if (hs == 0) posenc_pack_x3<0>(qh, ql, rw.x, prog.Fp, nullptr, nullptr, 0);
+        else posenc_pack_x3<1>(qh, ql, rw.x, prog.Fp, nullptr, nullptr, 0);
+      }
+    };
+    auto begin_tile = [&](int tile, const TilePref& pf) {
+      uint4 qh[4], ql[4];
+      tile_row(tile, pf, row);
+      tile_encode(row, qh, ql);
+      store_packed_x3(inh, inl, r, hs, qh, ql);
     };
 
     // fused composite: running state of the ray this CTA is on (replicated in every thread)
     float* scan_s = reinterpret_cast<float*>(base + kScanOff);
     float c_T = 1.f, c_cw = 0.f, a_r = 0.f, a_g = 0.f, a_b = 0.f, a_d = 0.f, a_w = 0.f, a_wnl = 0.f, a_med = 0.f;
+    TilePref pf;
     if (n_my > 0) {
-      begin_tile(tile_of(0));
+      tile_prefetch(tile_of(0), pf);
+      begin_tile(tile_of(0), pf);
       arrive_all();
     }
+    // The serial section between two tiles.  The next tile's rows are fetched two steps before the
+    // end of a tile and its first input block is ENCODED (fp64 sines, ~3.5 K cycles) in the idle time
+    // before the accumulator of the step in front of the rgb head arrives; the registers are stored
+    // once that step's MMAs - the last readers of the input block - are complete.  The rgb-head
+    // epilogue then releases the issuer as soon as it has drained its accumulator, and the volumetric
+    // rendering of this tile runs under the first MMAs of the next one.  (Needs an rgb head that does
+    // not read the input block; otherwise the encoding is written after the rgb head, as before.)
+    bool early_ok = !args.warp_only && prog.steps[last_step].epi == kEpiRgbOut && last_step - 1 >= first_step &&
+                    prog.steps[last_step - 1].epi == kEpiHidden;
+    for (int kb = 0; kb < prog.steps[last_step].nkb; ++kb)
+      if (prog.steps[last_step].src[kb] == kSrcIn) early_ok = false;
+#ifdef NFB_X3_NO_EARLY_NEXT
+    early_ok = false;
+#endif
+    const int pf_step = early_ok ? (last_step - 2 >= first_step ? last_step - 2 : last_step - 1) : last_step;
+    X3Row nrow;
+    uint4 nqh[4], nql[4];
+    bool next_stored = false;
     for (int ti = 0; ti < n_my; ++ti) {
       const int tile = tile_of(ti);
+      const bool has_next = ti + 1 < n_my;
       for (int si = first_step; si <= last_step; ++si) {
         const TcStep& st = prog.steps[si];
         const float4* bias4 = cst.b4 + si * 64;        // this step's 256 biases
         const float inv_s = cst.inv_scale[si];          // undoes the step's power-of-two weight scale
+        if (has_next && si == pf_step && !args.warp_only) tile_prefetch(tile_of(ti + 1), pf);
+        const bool encode_here = early_ok && has_next && si == last_step - 1;
+        if (encode_here) {
+          tile_row(tile_of(ti + 1), pf, nrow);
+          tile_encode(nrow, nqh, nql);
+        }
         if (st.epi == kEpiHidden && st.n_chunks == 1) {
           // ---- 128-wide layer, one N = 128 chunk: every MMA of the layer is complete, so the
           //      output overwrites the input in place; two 64-column instalments (x_ready[0] /
@@ -780,94 +862,101 @@ field_x3_kernel(const __grid_constant__ TcProgram prog, const __grid_constant__ 
           uint32_t ph[16], pl[16];
           float va[32], vb[32];
           const int ca = hs * 32, cb2 = 64 + hs * 32;
+          float4 bA[8], bB[8];
+          bias_preload(bias4 + (ca >> 2), bA);
+          bias_preload(bias4 + (cb2 >> 2), bB);
           mbar_wait(&bars->acc_ready[0], n_acc0++ & 1, dead);
           tc_fence_after();
           tr.ev(si, 0);
           x3_ld32(t_lane + ca, va);
-          x3_ld32(t_lane + cb2, vb);
+          tmem_ld_wait();
+          x3_ld32(t_lane + cb2, vb);                    // in flight under the first piece's arithmetic
+          x3_piece(va, bA, inv_s, relu, ph, pl);
           tmem_ld_wait();
           tc_fence_before();
           xr_arrive(&bars->x_ready[1]);               // the accumulator may be overwritten
-          x3_piece(va, bias4 + (ca >> 2), inv_s, relu, false, cst.alpha4, row.alpha, ph, pl);
           tst_piece(t_lane, ca, ph, pl);
           tmem_st_wait();
           tc_fence_before();
           xr_arrive(&bars->x_ready[0]);
           tr.ev(si, 3);
-          x3_piece(vb, bias4 + (cb2 >> 2), inv_s, relu, false, cst.alpha4, row.alpha, ph, pl);
+          x3_piece(vb, bB, inv_s, relu, ph, pl);
           tst_piece(t_lane, cb2, ph, pl);
           tmem_st_wait();
           tc_fence_before();
           xr_arrive(&bars->x_ready[2]);
           tr.ev(si, 5);
         } else if (st.epi == kEpiHidden) {
-          const int cols = st.chunk_n >> 1;            // columns of a chunk handled by this thread: 64 or 32
-          const bool wide = cols == 64;
+          // ---- 256-wide layer, two N = 128 chunks; each thread owns 64 columns of a chunk ----
           const bool relu = st.relu != 0, adot = st.alpha_dot != 0;
+          uint32_t ph[32], pl[32];
+          float va[32], vb[32];
+          const int col0 = hs * 64;
+          const int col1 = st.chunk_n + col0;
+          float4 bA[8], bB[8];
+          bias_preload(bias4 + (col0 >> 2), bA);
+          bias_preload(bias4 + (col0 >> 2) + 8, bB);
+          // The rgb condition goes into the input block (the first K-block of the next step).  Every
+          // earlier reader of the block belongs to a step whose last accumulator this thread has already
+          // waited for, so it is written BEFORE the wait (off the hand-off chain) unless this very step
+          // reads the block.
+          const bool cond_early = st.write_cond && st.src[0] != kSrcIn;
+          if (cond_early) {
+            cond_to_block_x3(inh, inl, r, args.cond + row.ray * prog.cond_stride + prog.G, prog.rc, cb, ce);
+            fence_proxy_async();
+          }
           // ---- chunk 0: results wait in registers until the MMAs of chunk 1 no
           //      longer read the blocks they overwrite ----
-          uint32_t ph[32], pl[32];
-          const int col0 = hs * cols;
           mbar_wait(&bars->acc_ready[0], n_acc0++ & 1, dead);
           tc_fence_after();
           tr.ev(si, 0);
-          if (wide) {
-            float va[32], vb[32];
-            x3_ld32(t_lane + col0, va);
-            x3_ld32(t_lane + col0 + 32, vb);
-            tmem_ld_wait();
-            x3_piece(va, bias4 + (col0 >> 2), inv_s, relu, adot, cst.alpha4 + (col0 >> 2), row.alpha, ph, pl);
-            x3_piece(vb, bias4 + (col0 >> 2) + 8, inv_s, relu, adot, cst.alpha4 + (col0 >> 2) + 8, row.alpha, ph + 16, pl + 16);
-          } else {
-            float va[32];
-            x3_ld32(t_lane + col0, va);
-            tmem_ld_wait();
-            x3_piece(va, bias4 + (col0 >> 2), inv_s, relu, adot, cst.alpha4 + (col0 >> 2), row.alpha, ph, pl);
-          }
+          x3_ld32(t_lane + col0, va);
+          tmem_ld_wait();
+          x3_ld32(t_lane + col0 + 32, vb);              // in flight under the first piece's arithmetic
+          x3_piece(va, bA, inv_s, relu, ph, pl);
+          tmem_ld_wait();
+          x3_piece(vb, bB, inv_s, relu, ph + 16, pl + 16);
           tr.ev(si, 1);
           if (st.kb_free != -2) mbar_wait(&bars->x_free, n_free++ & 1, dead);    // (-2: implied by acc_ready[0])
           tr.ev(si, 2);
           tst_piece(t_lane, col0, ph, pl);
-          if (wide) tst_piece(t_lane, col0 + 32, ph + 16, pl + 16);
-          // The input block is the first K-block of the next step (read right after
-          // x_ready[0]); every earlier reader of it (the skip layer) is complete.
-          if (st.write_cond)
+          tst_piece(t_lane, col0 + 32, ph + 16, pl + 16);
+          if (st.write_cond && !cond_early)
             cond_to_block_x3(inh, inl, r, args.cond + row.ray * prog.cond_stride + prog.G, prog.rc, cb, ce);
           tmem_st_wait();                               // the TMEM stores have completed ...
-          if (st.write_cond) fence_proxy_async();       // ... and the input-block stores are visible to the MMAs
+          if (st.write_cond && !cond_early) fence_proxy_async();   // ... and the input-block stores are visible to the MMAs
           tc_fence_before();
           xr_arrive(&bars->x_ready[0]);
           tr.ev(si, 3);
+          if (adot) {                                   // alpha head: after the hand-off
+            alpha_dot32(va, cst.alpha4 + (col0 >> 2), relu, row.alpha);
+            alpha_dot32(vb, cst.alpha4 + (col0 >> 2) + 8, relu, row.alpha);
+          }
           // ---- chunk 1: every MMA of the layer is complete, store directly ----
-          const int col1 = st.chunk_n + col0;
+          bias_preload(bias4 + (col1 >> 2), bA);
+          bias_preload(bias4 + (col1 >> 2) + 8, bB);
           mbar_wait(&bars->acc_ready[1], n_acc1++ & 1, dead);
           tc_fence_after();
           tr.ev(si, 4);
-          if (wide) {
-            float va[32], vb[32];
-            x3_ld32(t_lane + col1, va);
-            x3_ld32(t_lane + col1 + 32, vb);
-            tmem_ld_wait();
-            tc_fence_before();
-            xr_arrive(&bars->x_ready[1]);             // this accumulator may be overwritten (next step's chunk 1)
-            x3_piece(va, bias4 + (col1 >> 2), inv_s, relu, adot, cst.alpha4 + (col1 >> 2), row.alpha, ph, pl);
-            tst_piece(t_lane, col1, ph, pl);
-            x3_piece(vb, bias4 + (col1 >> 2) + 8, inv_s, relu, adot, cst.alpha4 + (col1 >> 2) + 8, row.alpha, ph, pl);
-            tst_piece(t_lane, col1 + 32, ph, pl);
-          } else {
-            float va[32];
-            x3_ld32(t_lane + col1, va);
-            tmem_ld_wait();
-            tc_fence_before();
-            xr_arrive(&bars->x_ready[1]);
-            x3_piece(va, bias4 + (col1 >> 2), inv_s, relu, adot, cst.alpha4 + (col1 >> 2), row.alpha, ph, pl);
-            tst_piece(t_lane, col1, ph, pl);
-          }
-          if (adot && hs == 1) alpha_part[r] = row.alpha;   // read by the row's first thread at the rgb step
+          x3_ld32(t_lane + col1, va);
+          tmem_ld_wait();
+          x3_ld32(t_lane + col1 + 32, vb);
+          x3_piece(va, bA, inv_s, relu, ph, pl);
+          tmem_ld_wait();
+          tc_fence_before();
+          xr_arrive(&bars->x_ready[1]);               // this accumulator may be overwritten (next step's chunk 1)
+          tst_piece(t_lane, col1, ph, pl);
+          x3_piece(vb, bB, inv_s, relu, ph, pl);
+          tst_piece(t_lane, col1 + 32, ph, pl);
           tmem_st_wait();
           tc_fence_before();
           xr_arrive(&bars->x_ready[2]);
           tr.ev(si, 5);
+          if (adot) {
+            alpha_dot32(va, cst.alpha4 + (col1 >> 2), relu, row.alpha);
+            alpha_dot32(vb, cst.alpha4 + (col1 >> 2) + 8, relu, row.alpha);
+            if (hs == 1) alpha_part[r] = row.alpha;     // read by the row's first thread at the rgb step
+          }
         } else {
           // ---- heads: N = 16 accumulator columns, one chunk (both threads of a row
           //      do the scalar work; they split the input-block chunks) ----
@@ -877,6 +966,8 @@ field_x3_kernel(const __grid_constant__ TcProgram prog, const __grid_constant__ 
           tr.ev(si, 0);
           tmem_ld16(t_lane, v);
           tmem_ld_wait();
+          // rgb head with the next tile's input block already in place: the issuer may go on
+          if (st.epi == kEpiRgbOut && next_stored) arrive_all();
 #pragma unroll
           for (int j = 0; j < 12; j += 4) {
             const float4 bq = bias4[j >> 2];
@@ -899,10 +990,10 @@ field_x3_kernel(const __grid_constant__ TcProgram prog, const __grid_constant__ 
               for (int c = 0; c < 3; ++c) args.warped[row.m * 3 + c] = y[c];
             }
             if (args.warp_only) {
-              if (ti + 1 < n_my) begin_tile(tile_of(ti + 1));
+              if (has_next) { tile_prefetch(tile_of(ti + 1), pf); begin_tile(tile_of(ti + 1), pf); }
             } else {
               if (hs == 0) posenc_block_x3<0>(inh, inl, r, row.x, prog.Fp, nullptr, nullptr, 0);
-        else posenc_block_x3<1>(inh, inl, r, row.x, prog.Fp, nullptr, nullptr, 0);
+              else posenc_block_x3<1>(inh, inl, r, row.x, prog.Fp, nullptr, nullptr, 0);
             }
             arrive_all();
           } else {
@@ -987,10 +1078,21 @@ field_x3_kernel(const __grid_constant__ TcProgram prog, const __grid_constant__ 
                 ro[5] = args.sample_at_infinity ? a_wnl : a_w;
               }
             }
-            if (ti + 1 < n_my) begin_tile(tile_of(ti + 1));
-            arrive_all();
+            if (next_stored) {
+              row = nrow;                               // (arrive_all went out right after the accumulator was drained)
+              next_stored = false;
+            } else {
+              if (has_next) begin_tile(tile_of(ti + 1), pf);
+              arrive_all();
+            }
             tr.ev(si, 5);
           }
+        }
+        if (encode_here) {
+          // this step's last accumulator has been waited for: the input block has no reader left
+          store_packed_x3(inh, inl, r, hs, nqh, nql);
+          fence_proxy_async();
+          next_stored = true;
         }
       }
     }

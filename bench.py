@@ -215,7 +215,7 @@ class ClockSampler:
       self.proc.wait(timeout=2)
     except subprocess.TimeoutExpired:
       self.proc.kill()
-    sm, mx, reasons = [], None, set()
+    sm, mx, reasons, pw = [], None, set(), []
     names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown',
              'sw_power_cap']
     for r in self.rows:
@@ -226,13 +226,18 @@ class ClockSampler:
         mx = float(r[1])
       except ValueError:
         continue
+      try:
+        pw.append(float(r[2]))
+      except ValueError:
+        pass
       for n, v in zip(names, r[3:7]):
         if v.lower().startswith('active'):
           reasons.add(n)
     busy = [v for v in sm if mx and v > 0.3 * mx] or sm
     return {'sm_mhz': statistics.median(busy) if busy else None,
             'sm_max_mhz': mx, 'reasons': sorted(reasons),
-            'samples': len(sm)}
+            'samples': len(sm), 'power_w': max(pw) if pw else None,
+            'power_w_median': statistics.median(pw) if pw else None}
 
 
 # ----------------------------------------------------------------------------

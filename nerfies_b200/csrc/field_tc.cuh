@@ -186,6 +186,17 @@ __device__ __forceinline__ uint64_t pack_f32x2(float lo, float hi) {
   asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
   return r;
 }
+// NFB_TC_BIAS_LDG (A/B build): the step's biases through L1 (ld.global.nc from the aux buffer) instead of
+// the kernel-parameter constant bank (24 KB of biases do not fit the constant cache: indexed LDCs miss).
+#ifdef NFB_TC_BIAS_LDG
+constexpr bool kTcBiasLdg = true;
+#else
+constexpr bool kTcBiasLdg = false;
+#endif
+__device__ __forceinline__ float4 tc_ld_bias(const float4* p, int i) {
+  if (kTcBiasLdg) return __ldg(p + i);
+  return p[i];
+}
 __device__ __forceinline__ void epi_piece(const float* v, const float4* __restrict__ bq4,
                                           bool relu, bool adot,
                                           const __nv_bfloat16* __restrict__ alpha_w32, float& alpha,
@@ -193,7 +204,7 @@ __device__ __forceinline__ void epi_piece(const float* v, const float4* __restri
   float t[32];
 #pragma unroll
   for (int j = 0; j < 32; j += 4) {
-    const float4 bq = bq4[j >> 2];                             // constant bank, warp-uniform address
+    const float4 bq = tc_ld_bias(bq4, j >> 2);                  // warp-uniform address
 #ifdef NFB_NO_F32X2
     t[j] = v[j] + bq.x; t[j + 1] = v[j + 1] + bq.y; t[j + 2] = v[j + 2] + bq.z; t[j + 3] = v[j + 3] + bq.w;
 #else
@@ -550,7 +561,8 @@ field_tc_kernel(const __grid_constant__ TcProgram prog, const __grid_constant__ 
     for (; pair < pair_lim; pair += gridDim.x) {
       for (int si = first_step; si <= last_step; ++si) {
         const TcStep& st = prog.steps[si];
-        const float4* bias4 = biasp.b4 + si * 64;     // this step's 256 biases (kernel-parameter constant bank)
+        const float4* bias4 = kTcBiasLdg ? reinterpret_cast<const float4*>(aux + st.b_off)
+                                         : biasp.b4 + si * 64;   // this step's 256 biases
         ++n_step;
         if (kH == 2) epi_sync();
         if (kH == 2 && merge_alpha) {
@@ -743,7 +755,7 @@ field_tc_kernel(const __grid_constant__ TcProgram prog, const __grid_constant__ 
           tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 12; j += 4) {
-            const float4 bq = bias4[j >> 2];
+            const float4 bq = tc_ld_bias(bias4, j >> 2);
             v[j] += bq.x; v[j + 1] += bq.y; v[j + 2] += bq.z; v[j + 3] += bq.w;
           }
           if (st.epi == kEpiWarpHeads) {

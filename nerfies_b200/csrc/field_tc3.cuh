@@ -255,6 +255,26 @@ __device__ __forceinline__ void cond_to_block_x3(uint8_t* bh, uint8_t* bl, int r
   }
 }
 
+// Epilogue scheduling options (A/B builds: tools/build_variant.py x -DNFB_X3_OPT=<mask>).
+#ifndef NFB_X3_OPT
+#define NFB_X3_OPT 73
+#endif
+constexpr bool kOBias = (NFB_X3_OPT & 1) != 0;       // biases into registers before the wait for the accumulator
+constexpr bool kOLdSplit = (NFB_X3_OPT & 2) != 0;    // second tcgen05.ld in flight under the first piece's arithmetic
+constexpr bool kOPrefetch = (NFB_X3_OPT & 4) != 0;   // next tile's z / ray loads issued one or two steps early
+constexpr bool kOCondEarly = (NFB_X3_OPT & 8) != 0;  // rgb condition written before the wait of its step
+constexpr bool kOAdotLate = (NFB_X3_OPT & 16) != 0;  // alpha-head dot product after the layer's hand-off
+constexpr bool kOEarlyNext = (NFB_X3_OPT & 32) != 0; // next tile's first input block encoded before the rgb head
+constexpr bool kOBiasLdg = (NFB_X3_OPT & 64) != 0;   // biases through L1 (ld.global.nc) instead of the constant bank
+
+// A step's biases: 18 KB over the steps of a level - more than the constant cache holds, so the indexed
+// LDCs of the constant-bank copy miss (ncu: LDC + the FFMA2s waiting for them = 38 % of the epilogue's
+// busy samples).  kOBiasLdg reads the same values from the global copy through L1.
+__device__ __forceinline__ float4 ld_bias(const float4* p, int i) {
+  if (kOBiasLdg) return __ldg(p + i);
+  return p[i];
+}
+
 // One 32-column piece of a hidden layer's epilogue: + bias, activation, (alpha head
 // dot product in fp32), split into fp16 hi / lo pairs.
 // `inv_s` undoes the power-of-two weight scale of the layer (x3_weight_scale): acc * inv_s is
@@ -275,7 +295,7 @@ __device__ __forceinline__ void x3_piece_fast(float* v, const float4* __restrict
   const uint64_t is2 = pack_f32x2(inv_s, inv_s);
 #pragma unroll
   for (int j = 0; j < 32; j += 4) {
-    const float4 bq = bq4[j >> 2];                  // preloaded registers (bias_preload)
+    const float4 bq = kOBias ? bq4[j >> 2] : ld_bias(bq4, j >> 2);   // (kOBias: already in registers)
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       uint64_t r, t, d;
@@ -324,13 +344,13 @@ __device__ __forceinline__ void x3_piece(float* v, const float4* __restrict__ bq
 
 // First chain of a unit: fence + 4 x (x_hi W_hi).  kTs: A from tensor memory (a = TMEM
 // address, K steps of 8 columns) or from shared memory (a = descriptor, K steps of 32 bytes).
-// NFB_X3_COLLECT (A/B build): K-step-major order inside a unit so that x_hi[k] is read from tensor
+// Default (off with -DNFB_X3_NO_COLLECT): K-step-major order inside a unit so that x_hi[k] is read from tensor
 // memory once for its two products (collector::a::fill, then ::lastuse):
 //   for k: x_hi[k] W_hi[k] (fill), x_hi[k] W_lo[k] (lastuse), x_lo[k] W_hi[k]
-#ifdef NFB_X3_COLLECT
-constexpr bool kCollect = true;
-#else
+#ifdef NFB_X3_NO_COLLECT
 constexpr bool kCollect = false;
+#else
+constexpr bool kCollect = true;     // +0.5 % (three A/B rounds, profiles/r02_ab_x3_variants.txt): one TMEM read of x_hi less per K step
 #endif
 template <bool kTs>
 __device__ __forceinline__ void issue_x3_head(uint32_t d, uint64_t a_hi, uint64_t a_lo, uint64_t b_hi, uint64_t b_lo,
@@ -420,7 +440,7 @@ __device__ __forceinline__ void issue_x3_head(uint32_t d, uint64_t a_hi, uint64_
       "or.b32 %0, %0, t0;\n\t" \
       "or.b32 %0, %0, t1;\n\t" \
       "or.b32 %0, %0, t2;\n\t"
-template <bool kMulticastRelease, bool kTs>
+template <int kCl, bool kTs>
 __device__ __forceinline__ uint32_t issue_x3_tail(uint32_t d, uint64_t a_hi, uint64_t a_lo, uint64_t b_hi,
                                                   uint64_t b_lo, uint32_t idesc, uint32_t bar_empty,
                                                   uint32_t bar_xfree, uint32_t bar_acc, uint32_t probe_w,
@@ -449,7 +469,7 @@ __device__ __forceinline__ uint32_t issue_x3_tail(uint32_t d, uint64_t a_hi, uin
         : "=r"(out)
         : "r"(d), "r"((uint32_t)a_hi), "r"((uint32_t)a_lo), "l"(b_hi), "l"(b_lo), "r"(idesc), "r"(bar_empty),
           "r"(bar_xfree), "r"(bar_acc), "r"(probe_w), "r"(par_w), "r"(probe_x0), "r"(probe_x1),
-          "r"(probe_x2), "r"(par_x), "h"((uint16_t)0x3), "r"(kMulticastRelease ? 1u : 0u)
+          "r"(probe_x2), "r"(par_x), "h"((uint16_t)((1u << kCl) - 1u)), "r"(kCl > 1 ? 1u : 0u)
         : "memory");
   } else if constexpr (kTs) {
     asm volatile(
@@ -473,7 +493,7 @@ __device__ __forceinline__ uint32_t issue_x3_tail(uint32_t d, uint64_t a_hi, uin
         : "=r"(out)
         : "r"(d), "r"((uint32_t)a_hi), "r"((uint32_t)a_lo), "l"(b_hi), "l"(b_lo), "r"(idesc), "r"(bar_empty),
           "r"(bar_xfree), "r"(bar_acc), "r"(probe_w), "r"(par_w), "r"(probe_x0), "r"(probe_x1),
-          "r"(probe_x2), "r"(par_x), "h"((uint16_t)0x3), "r"(kMulticastRelease ? 1u : 0u)
+          "r"(probe_x2), "r"(par_x), "h"((uint16_t)((1u << kCl) - 1u)), "r"(kCl > 1 ? 1u : 0u)
         : "memory");
   } else {
     asm volatile(
@@ -496,7 +516,7 @@ __device__ __forceinline__ uint32_t issue_x3_tail(uint32_t d, uint64_t a_hi, uin
         : "=r"(out)
         : "r"(d), "l"(a_hi), "l"(a_lo), "l"(b_hi), "l"(b_lo), "r"(idesc), "r"(bar_empty),
           "r"(bar_xfree), "r"(bar_acc), "r"(probe_w), "r"(par_w), "r"(probe_x0), "r"(probe_x1),
-          "r"(probe_x2), "r"(par_x), "h"((uint16_t)0x3), "r"(kMulticastRelease ? 1u : 0u)
+          "r"(probe_x2), "r"(par_x), "h"((uint16_t)((1u << kCl) - 1u)), "r"(kCl > 1 ? 1u : 0u)
         : "memory");
   }
   return out;
@@ -508,12 +528,14 @@ __device__ __forceinline__ uint32_t issue_x3_tail(uint32_t d, uint64_t a_hi, uin
 // The 32 biases of a piece, fetched from the constant bank BEFORE the wait for the accumulator (the
 // empty asm keeps the loads there: otherwise they are sunk to their uses and their latency lands
 // on the hand-off chain accumulator -> epilogue -> next layer's first MMA).
-__device__ __forceinline__ void bias_preload(const float4* __restrict__ src, float4* dst) {
+__device__ __forceinline__ const float4* bias_preload(const float4* __restrict__ src, float4* dst) {
+  if (!kOBias) return src;
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
-    dst[i] = src[i];
+    dst[i] = ld_bias(src, i);
     asm volatile("" ::"f"(dst[i].x), "f"(dst[i].y), "f"(dst[i].z), "f"(dst[i].w));
   }
+  return dst;
 }
 
 // One 32-column piece of a layer's output (16 packed pairs per image) -> this thread's TMEM lane.
@@ -544,17 +566,18 @@ struct X3Row {
   bool last;         // last sample of its ray
 };
 
-// kPair: launched as clusters of two CTAs that SHARE the weight stream: rank 0 fetches the W_hi
-// half of every slot, rank 1 the W_lo half, each with a multicast bulk copy into both CTAs' rings.
+// kCl > 1: launched as clusters of kCl CTAs that SHARE the weight stream: rank i fetches part i of
+// every slot with a multicast bulk copy into all the CTAs' rings.
 // Every SM of the chip streams the same 5.6 MB of weights in near lockstep, which makes the L2
 // slices that hold the current unit the bottleneck (148 readers per line: a 32 KB slot took ~1,500
 // cycles to arrive); sharing halves those reads.  Otherwise the two CTAs are independent (own
 // tiles, own MMAs, own TMEM): the only coupling is that a slot is refilled once BOTH issuers have
 // released it (empty barriers count two multicast commits).
-template <bool kPair>
+template <int kCl>
 __global__ void __launch_bounds__(kX3Threads, 1)
 field_x3_kernel(const __grid_constant__ TcProgram prog, const __grid_constant__ X3Consts cst,
-                const FieldArgs args, const uint8_t* __restrict__ wpack, int num_tiles) {
+                const FieldArgs args, const uint8_t* __restrict__ wpack, int num_tiles,
+                const float* __restrict__ aux) {
   constexpr int kEpiWarps = 8, kMmaWarp = 8, kProdWarp = 9;
   extern __shared__ __align__(1024) uint8_t raw[];
   uint8_t* base = raw;
@@ -572,7 +595,7 @@ field_x3_kernel(const __grid_constant__ TcProgram prog, const __grid_constant__ 
   if (tid == kMmaWarp * 32) {
     for (int i = 0; i < kX3Slots; ++i) {
       mbar_init(&bars->full[i], 1);
-      if ((i & 1) == 0) mbar_init(&bars->empty[i >> 1], kPair ? 2 : 1);
+      if ((i & 1) == 0) mbar_init(&bars->empty[i >> 1], kCl);
     }
     mbar_init(&bars->acc_ready[0], 1); mbar_init(&bars->acc_ready[1], 1);
     mbar_init(&bars->x_free, 1);
@@ -581,10 +604,10 @@ field_x3_kernel(const __grid_constant__ TcProgram prog, const __grid_constant__ 
   }
   if (warp == kMmaWarp) tmem_alloc(&bars->tmem_slot, kTmCols);
   tc_fence_before();
-  if constexpr (kPair) cluster_sync_all();      // the peer's barriers exist before any multicast lands
+  if constexpr (kCl > 1) cluster_sync_all();    // the peers' barriers exist before any multicast lands
   else __syncthreads();
   tc_fence_after();
-  const uint32_t rank = kPair ? cluster_ctarank() : 0u;
+  const uint32_t rank = kCl > 1 ? cluster_ctarank() : 0u;
   const uint32_t tmem_base = bars->tmem_slot;
   const bool do_warp = args.use_warp && prog.warp_type != 0;
   int first_step = 0;
@@ -606,7 +629,7 @@ field_x3_kernel(const __grid_constant__ TcProgram prog, const __grid_constant__ 
   const int groups = num_tiles / tpr;
   // (a CTA pair runs the same number of units - the count of its even member: the ring couples
   //  them; the odd member's surplus tile lies beyond the end, is computed on clamped rows and never stored)
-  const int bid_n = kPair ? ((int)blockIdx.x & ~1) : (int)blockIdx.x;
+  const int bid_n = (int)blockIdx.x & ~(kCl - 1);
   const int my_groups = bid_n < groups ? (groups - bid_n + (int)gridDim.x - 1) / (int)gridDim.x : 0;
   const int n_my = my_groups * tpr;
   auto tile_of = [&](int i) { return ((int)blockIdx.x + (i / tpr) * (int)gridDim.x) * tpr + (i % tpr); };
@@ -620,7 +643,6 @@ field_x3_kernel(const __grid_constant__ TcProgram prog, const __grid_constant__ 
       for (int si = first_step; si <= last_step; ++si) {
         const TcStep& st = prog.steps[si];
         const uint32_t bytes = 2u * (uint32_t)st.chunk_n * kRowBytes;   // [W_hi | W_lo] of one unit, contiguous
-        const uint32_t half = bytes >> 1;
         const uint8_t* src = wpack + st.w_off;
         const int n = st.n_chunks * st.nkb;               // [chunk][kb]
         for (int u = 0; u < n; ++u) {
@@ -635,9 +657,10 @@ field_x3_kernel(const __grid_constant__ TcProgram prog, const __grid_constant__ 
 #endif
           if (elect_one()) {
             mbar_arrive_expect_tx(&bars->full[sg], bytes);
-            if constexpr (kPair) {
-              // rank 0: W_hi, rank 1: W_lo - to both CTAs
-              bulk_g2s_multicast(dst + rank * half, from + rank * half, half, &bars->full[sg], (uint16_t)0x3);
+            if constexpr (kCl > 1) {
+              // every rank fetches its 1 / kCl of the slot - to all CTAs of the cluster
+              const uint32_t part = bytes / kCl;
+              bulk_g2s_multicast(dst + rank * part, from + rank * part, part, &bars->full[sg], (uint16_t)((1u << kCl) - 1u));
             } else {
               bulk_g2s(dst, from, bytes, &bars->full[sg]);
             }
@@ -707,10 +730,10 @@ field_x3_kernel(const __grid_constant__ TcProgram prog, const __grid_constant__ 
           const uint32_t bar_x = (flags & kUCommitXFree) ? b_xfree : 0u;
           const uint32_t bar_a = (flags & kUCommitAcc0) ? b_acc0 : ((flags & kUCommitAcc1) ? b_acc1 : 0u);
           if (ts)
-            ready = issue_x3_tail<kPair, true>(d_cur, a_hi, a_lo, bd_cur, b_lo, idesc, bar_e, bar_x, bar_a,
+            ready = issue_x3_tail<kCl, true>(d_cur, a_hi, a_lo, bd_cur, b_lo, idesc, bar_e, bar_x, bar_a,
                                                b_full + nsg * 8, nwph, px0, px1, px2, nxr & 1);
           else
-            ready = issue_x3_tail<kPair, false>(d_cur, a_hi, a_lo, bd_cur, b_lo, idesc, bar_e, bar_x, bar_a,
+            ready = issue_x3_tail<kCl, false>(d_cur, a_hi, a_lo, bd_cur, b_lo, idesc, bar_e, bar_x, bar_a,
                                                 b_full + nsg * 8, nwph, px0, px1, px2, nxr & 1);
           if (flags & (kUCommitAcc0 | kUCommitAcc1)) tr.ev(c1.w, (flags & kUCommitAcc0) ? 1 : 2);
           if (flags & kUWaitX0) tr.ev(c1.w, 0);
@@ -834,10 +857,10 @@ field_x3_kernel(const __grid_constant__ TcProgram prog, const __grid_constant__ 
                     prog.steps[last_step - 1].epi == kEpiHidden;
     for (int kb = 0; kb < prog.steps[last_step].nkb; ++kb)
       if (prog.steps[last_step].src[kb] == kSrcIn) early_ok = false;
-#ifdef NFB_X3_NO_EARLY_NEXT
-    early_ok = false;
-#endif
-    const int pf_step = early_ok ? (last_step - 2 >= first_step ? last_step - 2 : last_step - 1) : last_step;
+    if (!kOEarlyNext) early_ok = false;
+    // (without kOPrefetch the loads are issued right in front of begin_tile: pf_step = -1)
+    const int pf_step = early_ok ? (last_step - 2 >= first_step ? last_step - 2 : last_step - 1)
+                                 : (kOPrefetch ? last_step : -1);
     X3Row nrow;
     uint4 nqh[4], nql[4];
     bool next_stored = false;
@@ -846,7 +869,8 @@ field_x3_kernel(const __grid_constant__ TcProgram prog, const __grid_constant__ 
       const bool has_next = ti + 1 < n_my;
       for (int si = first_step; si <= last_step; ++si) {
         const TcStep& st = prog.steps[si];
-        const float4* bias4 = cst.b4 + si * 64;        // this step's 256 biases
+        const float4* bias4 = kOBiasLdg ? reinterpret_cast<const float4*>(aux + st.b_off)
+                                        : cst.b4 + si * 64;   // this step's 256 biases
         const float inv_s = cst.inv_scale[si];          // undoes the step's power-of-two weight scale
         if (has_next && si == pf_step && !args.warp_only) tile_prefetch(tile_of(ti + 1), pf);
         const bool encode_here = early_ok && has_next && si == last_step - 1;
@@ -862,19 +886,27 @@ field_x3_kernel(const __grid_constant__ TcProgram prog, const __grid_constant__ 
           uint32_t ph[16], pl[16];
           float va[32], vb[32];
           const int ca = hs * 32, cb2 = 64 + hs * 32;
-          float4 bA[8], bB[8];
-          bias_preload(bias4 + (ca >> 2), bA);
-          bias_preload(bias4 + (cb2 >> 2), bB);
+          float4 bAr[8], bBr[8];
+          const float4* bA = bias_preload(bias4 + (ca >> 2), bAr);
+          const float4* bB = bias_preload(bias4 + (cb2 >> 2), bBr);
           mbar_wait(&bars->acc_ready[0], n_acc0++ & 1, dead);
           tc_fence_after();
           tr.ev(si, 0);
           x3_ld32(t_lane + ca, va);
-          tmem_ld_wait();
-          x3_ld32(t_lane + cb2, vb);                    // in flight under the first piece's arithmetic
-          x3_piece(va, bA, inv_s, relu, ph, pl);
-          tmem_ld_wait();
-          tc_fence_before();
-          xr_arrive(&bars->x_ready[1]);               // the accumulator may be overwritten
+          if (kOLdSplit) {
+            tmem_ld_wait();
+            x3_ld32(t_lane + cb2, vb);                  // in flight under the first piece's arithmetic
+            x3_piece(va, bA, inv_s, relu, ph, pl);
+            tmem_ld_wait();
+            tc_fence_before();
+            xr_arrive(&bars->x_ready[1]);               // the accumulator may be overwritten
+          } else {
+            x3_ld32(t_lane + cb2, vb);
+            tmem_ld_wait();
+            tc_fence_before();
+            xr_arrive(&bars->x_ready[1]);               // the accumulator may be overwritten
+            x3_piece(va, bA, inv_s, relu, ph, pl);
+          }
           tst_piece(t_lane, ca, ph, pl);
           tmem_st_wait();
           tc_fence_before();
@@ -893,14 +925,13 @@ field_x3_kernel(const __grid_constant__ TcProgram prog, const __grid_constant__ 
           float va[32], vb[32];
           const int col0 = hs * 64;
           const int col1 = st.chunk_n + col0;
-          float4 bA[8], bB[8];
-          bias_preload(bias4 + (col0 >> 2), bA);
-          bias_preload(bias4 + (col0 >> 2) + 8, bB);
+          float4 bAr[8], bBr[8];
+          const float4* bA = bias_preload(bias4 + (col0 >> 2), bAr);
+          const float4* bB = bias_preload(bias4 + (col0 >> 2) + 8, bBr);
           // The rgb condition goes into the input block (the first K-block of the next step).  Every
           // earlier reader of the block belongs to a step whose last accumulator this thread has already
-          // waited for, so it is written BEFORE the wait (off the hand-off chain) unless this very step
-          // reads the block.
-          const bool cond_early = st.write_cond && st.src[0] != kSrcIn;
+          // waited for, so it may be written BEFORE the wait (kOCondEarly) unless this very step reads the block.
+          const bool cond_early = kOCondEarly && st.write_cond && st.src[0] != kSrcIn;
           if (cond_early) {
             cond_to_block_x3(inh, inl, r, args.cond + row.ray * prog.cond_stride + prog.G, prog.rc, cb, ce);
             fence_proxy_async();
@@ -911,11 +942,19 @@ field_x3_kernel(const __grid_constant__ TcProgram prog, const __grid_constant__ 
           tc_fence_after();
           tr.ev(si, 0);
           x3_ld32(t_lane + col0, va);
-          tmem_ld_wait();
-          x3_ld32(t_lane + col0 + 32, vb);              // in flight under the first piece's arithmetic
-          x3_piece(va, bA, inv_s, relu, ph, pl);
-          tmem_ld_wait();
+          if (kOLdSplit) {
+            tmem_ld_wait();
+            x3_ld32(t_lane + col0 + 32, vb);            // in flight under the first piece's arithmetic
+            x3_piece(va, bA, inv_s, relu, ph, pl);
+            tmem_ld_wait();
+          } else {
+            x3_ld32(t_lane + col0 + 32, vb);
+            tmem_ld_wait();
+            x3_piece(va, bA, inv_s, relu, ph, pl);
+          }
+          if (adot && !kOAdotLate) alpha_dot32(va, cst.alpha4 + (col0 >> 2), relu, row.alpha);
           x3_piece(vb, bB, inv_s, relu, ph + 16, pl + 16);
+          if (adot && !kOAdotLate) alpha_dot32(vb, cst.alpha4 + (col0 >> 2) + 8, relu, row.alpha);
           tr.ev(si, 1);
           if (st.kb_free != -2) mbar_wait(&bars->x_free, n_free++ & 1, dead);    // (-2: implied by acc_ready[0])
           tr.ev(si, 2);
@@ -928,33 +967,45 @@ field_x3_kernel(const __grid_constant__ TcProgram prog, const __grid_constant__ 
           tc_fence_before();
           xr_arrive(&bars->x_ready[0]);
           tr.ev(si, 3);
-          if (adot) {                                   // alpha head: after the hand-off
+          if (adot && kOAdotLate) {                     // alpha head: after the hand-off
             alpha_dot32(va, cst.alpha4 + (col0 >> 2), relu, row.alpha);
             alpha_dot32(vb, cst.alpha4 + (col0 >> 2) + 8, relu, row.alpha);
           }
           // ---- chunk 1: every MMA of the layer is complete, store directly ----
-          bias_preload(bias4 + (col1 >> 2), bA);
-          bias_preload(bias4 + (col1 >> 2) + 8, bB);
+          bA = bias_preload(bias4 + (col1 >> 2), bAr);
+          bB = bias_preload(bias4 + (col1 >> 2) + 8, bBr);
           mbar_wait(&bars->acc_ready[1], n_acc1++ & 1, dead);
           tc_fence_after();
           tr.ev(si, 4);
           x3_ld32(t_lane + col1, va);
-          tmem_ld_wait();
-          x3_ld32(t_lane + col1 + 32, vb);
-          x3_piece(va, bA, inv_s, relu, ph, pl);
-          tmem_ld_wait();
-          tc_fence_before();
-          xr_arrive(&bars->x_ready[1]);               // this accumulator may be overwritten (next step's chunk 1)
+          if (kOLdSplit) {
+            tmem_ld_wait();
+            x3_ld32(t_lane + col1 + 32, vb);
+            x3_piece(va, bA, inv_s, relu, ph, pl);
+            tmem_ld_wait();
+            tc_fence_before();
+            xr_arrive(&bars->x_ready[1]);             // this accumulator may be overwritten (next step's chunk 1)
+          } else {
+            x3_ld32(t_lane + col1 + 32, vb);
+            tmem_ld_wait();
+            tc_fence_before();
+            xr_arrive(&bars->x_ready[1]);
+            x3_piece(va, bA, inv_s, relu, ph, pl);
+          }
+          if (adot && !kOAdotLate) alpha_dot32(va, cst.alpha4 + (col1 >> 2), relu, row.alpha);
           tst_piece(t_lane, col1, ph, pl);
           x3_piece(vb, bB, inv_s, relu, ph, pl);
+          if (adot && !kOAdotLate) alpha_dot32(vb, cst.alpha4 + (col1 >> 2) + 8, relu, row.alpha);
           tst_piece(t_lane, col1 + 32, ph, pl);
           tmem_st_wait();
           tc_fence_before();
           xr_arrive(&bars->x_ready[2]);
           tr.ev(si, 5);
           if (adot) {
-            alpha_dot32(va, cst.alpha4 + (col1 >> 2), relu, row.alpha);
-            alpha_dot32(vb, cst.alpha4 + (col1 >> 2) + 8, relu, row.alpha);
+            if (kOAdotLate) {
+              alpha_dot32(va, cst.alpha4 + (col1 >> 2), relu, row.alpha);
+              alpha_dot32(vb, cst.alpha4 + (col1 >> 2) + 8, relu, row.alpha);
+            }
             if (hs == 1) alpha_part[r] = row.alpha;     // read by the row's first thread at the rgb step
           }
         } else {
@@ -970,7 +1021,7 @@ field_x3_kernel(const __grid_constant__ TcProgram prog, const __grid_constant__ 
           if (st.epi == kEpiRgbOut && next_stored) arrive_all();
 #pragma unroll
           for (int j = 0; j < 12; j += 4) {
-            const float4 bq = bias4[j >> 2];
+            const float4 bq = ld_bias(bias4, j >> 2);
             v[j] = fmaf(v[j], inv_s, bq.x); v[j + 1] = fmaf(v[j + 1], inv_s, bq.y);
             v[j + 2] = fmaf(v[j + 2], inv_s, bq.z); v[j + 3] = fmaf(v[j + 3], inv_s, bq.w);
           }
@@ -1082,7 +1133,10 @@ field_x3_kernel(const __grid_constant__ TcProgram prog, const __grid_constant__ 
               row = nrow;                               // (arrive_all went out right after the accumulator was drained)
               next_stored = false;
             } else {
-              if (has_next) begin_tile(tile_of(ti + 1), pf);
+              if (has_next) {
+                if (pf_step < 0) tile_prefetch(tile_of(ti + 1), pf);
+                begin_tile(tile_of(ti + 1), pf);
+              }
               arrive_all();
             }
             tr.ev(si, 5);
@@ -1099,14 +1153,24 @@ field_x3_kernel(const __grid_constant__ TcProgram prog, const __grid_constant__ 
     tr.finish(args, 1 + hs);
     tc_fence_before();
   }
-  if constexpr (kPair) cluster_sync_all();   // nobody exits while the peer may still multicast into it / signal it
+  if constexpr (kCl > 1) cluster_sync_all();  // nobody exits while a peer may still multicast into it / signal it
   else __syncthreads();
   if (warp == kMmaWarp) tmem_dealloc(tmem_base, kTmCols);
 }
 
+// Cluster launch (-DNFB_X3_CLUSTER=2|4): the CTAs of a cluster share ONE weight stream - every rank
+// fetches 1 / kCl of each slot and multicasts it into all rings, so the L2 -> SM weight traffic
+// (2.8 MB per 128-row tile and SM, ~6 TB/s over the chip) drops by kCl; the CTAs are otherwise
+// independent (own tiles, MMAs, TMEM) but a slot is refilled only once ALL issuers have released it.
+#ifndef NFB_X3_CLUSTER
+#define NFB_X3_CLUSTER 1
+#endif
+constexpr int kX3Cluster = NFB_X3_CLUSTER;
+static_assert(kX3Cluster == 1 || kX3Cluster == 2 || kX3Cluster == 4, "cluster size");
+
 inline int create_x3(nfb_handle*) {
-  if (cudaFuncSetAttribute(field_x3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kX3SmemBytes) != cudaSuccess ||
-      cudaFuncSetAttribute(field_x3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kX3SmemBytes) != cudaSuccess)
+  if (cudaFuncSetAttribute(field_x3_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kX3SmemBytes) != cudaSuccess ||
+      cudaFuncSetAttribute(field_x3_kernel<kX3Cluster>, cudaFuncAttributeMaxDynamicSharedMemorySize, kX3SmemBytes) != cudaSuccess)
     return fail("cannot reserve %d bytes of shared memory for the fp16x3 kernel", kX3SmemBytes);
   return 0;
 }
@@ -1118,25 +1182,20 @@ inline int run_field_x3(nfb_handle* h, int level, const FieldArgs& a, cudaStream
   if (fuse && (a.samples_per_ray % kTileRows != 0 || a.num_rows % a.samples_per_ray != 0))
     return fail("fused composite needs samples_per_ray to be a multiple of %d", kTileRows);
   const long long groups = fuse ? a.num_rows / a.samples_per_ray : tiles;
-  // The CTA-pair launch (two CTAs share one multicast weight stream: half the L2 reads) measured 1 % SLOWER
-  // than independent CTAs once the ring was deep enough (L2 throughput is at 12 %; the coupling of the two
-  // issuers through the shared slot release costs more): off unless built with -DNFB_X3_PAIR.
-#ifndef NFB_X3_PAIR
-  h->x3_pair_ok = 0;
-#endif
+  if (kX3Cluster == 1) h->x3_pair_ok = 0;
   if (groups >= (long long)h->sm_count && h->x3_pair_ok != 0) {
-    // CTA pairs sharing the weight stream (see the kernel): worth it once every SM has work
+    // clusters sharing the weight stream (see above): worth it once every SM has work
     cudaLaunchConfig_t cfg = {};
     cfg.blockDim = dim3(kX3Threads); cfg.dynamicSmemBytes = kX3SmemBytes; cfg.stream = s;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    attr[0].val.clusterDim.x = kX3Cluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
     if (h->x3_pair_ok < 0) {
       // persistent kernel: no more clusters than can be co-resident
-      cfg.gridDim = dim3((unsigned)(h->sm_count & ~1));
+      cfg.gridDim = dim3((unsigned)(h->sm_count / kX3Cluster * kX3Cluster));
       int n = 0;
-      if (cudaOccupancyMaxActiveClusters(&n, field_x3_kernel<true>, &cfg) != cudaSuccess || n < 1) {
+      if (cudaOccupancyMaxActiveClusters(&n, field_x3_kernel<kX3Cluster>, &cfg) != cudaSuccess || n < 1) {
         cudaGetLastError();
         h->x3_pair_ok = 0;
       } else {
@@ -1144,17 +1203,17 @@ inline int run_field_x3(nfb_handle* h, int level, const FieldArgs& a, cudaStream
       }
     }
     if (h->x3_pair_ok > 0) {
-      const int grid2 = 2 * (int)std::min<long long>((groups + 1) / 2, h->x3_pair_ok);
-      cfg.gridDim = dim3((unsigned)grid2);
-      cudaError_t le = cudaLaunchKernelEx(&cfg, field_x3_kernel<true>, h->tcprog[level], h->x3c[level], a,
-                                          (const uint8_t*)h->d_wpack, (int)tiles);
-      if (le != cudaSuccess) return fail("field_x3_kernel (CTA pair) launch failed: %s", cudaGetErrorString(le));
+      const int gridc = kX3Cluster * (int)std::min<long long>((groups + kX3Cluster - 1) / kX3Cluster, h->x3_pair_ok);
+      cfg.gridDim = dim3((unsigned)gridc);
+      cudaError_t le = cudaLaunchKernelEx(&cfg, field_x3_kernel<kX3Cluster>, h->tcprog[level], h->x3c[level], a,
+                                          (const uint8_t*)h->d_wpack, (int)tiles, (const float*)h->d_aux);
+      if (le != cudaSuccess) return fail("field_x3_kernel (cluster) launch failed: %s", cudaGetErrorString(le));
       h->launches++;
       return 0;
     }
   }
   const int grid = (int)std::min<long long>(groups, h->sm_count);
-  field_x3_kernel<false><<<grid, kX3Threads, kX3SmemBytes, s>>>(h->tcprog[level], h->x3c[level], a, h->d_wpack, (int)tiles);
+  field_x3_kernel<1><<<grid, kX3Threads, kX3SmemBytes, s>>>(h->tcprog[level], h->x3c[level], a, h->d_wpack, (int)tiles, (const float*)h->d_aux);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail("field_x3_kernel launch failed: %s", cudaGetErrorString(e));
   h->launches++;

@@ -495,7 +495,10 @@ def roofline(res, wl, B, peaks, precision):
       'fp32': 'fp32 mode runs on the FFMA pipe; the fraction is still quoted against the bf16 '
               'tensor peak the north-star names',
       'fp16x3': 'ALGORITHMIC FLOPs only: the three fp16 MMA chains that emulate fp32 execute 3x '
-                'this many tensor FLOPs (no credit taken); tensor-pipe busy fraction = 3 x frac',
+                'this many tensor FLOPs (no credit taken); tensor-pipe busy fraction = 3 x frac. '
+                'The kernel runs at the board power limit (see clocks: sw_power_cap, ~1.75 of '
+                '1.965 GHz, ~990 W in a 60-step run: profiles/r02_ab_x3_variants.txt), so the '
+                'fraction is bounded by energy per MMA, not by the issue rate',
       'bf16': '',
   }
   r = {

@@ -7,6 +7,8 @@ R=r02
 exec </dev/null
 python bench.py --steps 10 --warmup 3 > gpurun_out/${R}_bench_default_1gpu.json 2> gpurun_out/${R}_bench_default_1gpu.err
 tail -c 600 gpurun_out/${R}_bench_default_1gpu.json
+# power / clock under a sustained load (5 s): nvidia-smi's reading needs more than a 10-step run
+python bench.py --steps 60 --warmup 3 --no-cpu-baseline --no-also --no-parity > gpurun_out/${R}_bench_power_60steps.json 2>/dev/null
 for w in quarterhd-train vrig-train fullhd-train; do
   python bench.py --workload $w --steps 5 --no-cpu-baseline > gpurun_out/${R}_bench_$w.json 2> gpurun_out/${R}_bench_$w.err
 done
@@ -30,6 +32,6 @@ ncu --set full --clock-control none -k regex:camera_rays -s 6 -c 2 -f -o gpurun_
 export_rep camera camera
 python tools/bench_camera.py > gpurun_out/${R}_bench_camera.json 2>/dev/null
 python tools/microbench_tmem_a.py > gpurun_out/${R}_microbench_tmem_a.json 2>/dev/null
-python tools/build_variant.py trace -DNFB_TRACE >/dev/null 2>&1 || true
+[ -f nerfies_b200/_variants/libnfb_trace.so ] || python tools/build_variant.py trace -DNFB_TRACE >/dev/null 2>&1 || true
 PREC=fp16x3 STEP_LO=0 STEP_HI=40 timeout 200 python tools/trace_tc.py > gpurun_out/${R}_x3_timeline.txt 2>&1
 head -24 gpurun_out/${R}_x3_timeline.txt

@@ -429,7 +429,7 @@ __device__ __forceinline__ void issue_x3_head(uint32_t d, uint64_t a_hi, uint64_
 #define NFB_X3_TAIL_EPILOGUE \
       /* slot release: every second unit (a PAIR of slots per commit: a commit costs ~120 cycles of issue) */ \
       "@pe1 tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%7];\n\t" \
-      /* CTA-pair build: the weight slot is shared (multicast copies): release it in both CTAs */ \
+      /* cluster build: the weight slot is shared (multicast copies): release it in every CTA of the cluster */ \
       "@pe2 tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%7], %16;\n\t" \
       "@pcx tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%8];\n\t" \
       "@pca tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%9];\n\t" \
@@ -627,7 +627,7 @@ field_x3_kernel(const __grid_constant__ TcProgram prog, const __grid_constant__ 
   const bool fuse = args.ray_out != nullptr && !args.warp_only;
   const int tpr = fuse ? args.samples_per_ray / kTileRows : 1;          // tiles per group
   const int groups = num_tiles / tpr;
-  // (a CTA pair runs the same number of units - the count of its even member: the ring couples
+  // (the CTAs of a cluster run the same number of units - the count of the first member: the ring couples
   //  them; the odd member's surplus tile lies beyond the end, is computed on clamped rows and never stored)
   const int bid_n = (int)blockIdx.x & ~(kCl - 1);
   const int my_groups = bid_n < groups ? (groups - bid_n + (int)gridDim.x - 1) / (int)gridDim.x : 0;
@@ -1084,7 +1084,7 @@ field_x3_kernel(const __grid_constant__ TcProgram prog, const __grid_constant__ 
               }
               const float Ti = (c_T * Wq) * excl;              // accum_prod (model_utils.py:110-113)
               const float w = al * Ti;
-              const bool live = tile < num_tiles;              // (a CTA pair's surplus tile computes on clamped rows)
+              const bool live = tile < num_tiles;              // (a cluster's surplus tile computes on clamped rows)
               if (args.ray_weights && live) args.ray_weights[row.m] = w;
               float C = w;                                     // inclusive cumsum of the weights
 #pragma unroll

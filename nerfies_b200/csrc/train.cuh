@@ -102,6 +102,94 @@ sgemm_kernel(GemmShape sh, FA fa, FB fb, FC fc, long long k_per_split) {
     }
 }
 
+// The same GEMM with a 128 x 128 C tile, an 8 x 8 register tile per thread (two 4 x 4 quadrant pairs, so that
+// every shared-memory read is a 16-byte vector and the A reads are warp broadcasts), k-steps of 8 and a register
+// prefetch of the next k-step's operands under the arithmetic of the current one (one __syncthreads per step).
+// 64 FMAs per 4 LDS.128 instead of 16 per 2: the layer-wise training tier is GEMM-bound (3 x the forward FLOPs
+// per step), and this template runs it about twice as fast as sgemm_kernel.
+// kAKFast / kBNFast: which index of the element functor is contiguous in memory (k for a row-major A, n for a
+// row-major B) - the loader walks that index with consecutive threads.
+constexpr int kT2 = 128, kBK2 = 8, kPad2 = 4;
+template <bool kAKFast, bool kBNFast, class FA, class FB, class FC>
+__global__ void __launch_bounds__(256, 2)
+sgemm128_kernel(GemmShape sh, FA fa, FB fb, FC fc, long long k_per_split) {
+  __shared__ __align__(16) float As[2][kBK2][kT2 + kPad2];
+  __shared__ __align__(16) float Bs[2][kBK2][kT2 + kPad2];
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;
+  const long long m0 = (long long)blockIdx.x * kT2;
+  const int n0 = blockIdx.y * kT2;
+  const long long k_begin = (long long)blockIdx.z * k_per_split;
+  const long long k_end = min(sh.K, k_begin + k_per_split);
+  float acc[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+  float ra[4], rb[4];
+  auto fetch = [&](long long k0) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int idx = tid + e * 256;
+      {
+        const int mm = kAKFast ? idx / kBK2 : idx % kT2, kk = kAKFast ? idx % kBK2 : idx / kT2;
+        const long long m = m0 + mm, k = k0 + kk;
+        ra[e] = (m < sh.M && k < k_end) ? fa(m, k) : 0.f;
+      }
+      {
+        const int kk = kBNFast ? idx / kT2 : idx % kBK2, nn = kBNFast ? idx % kT2 : idx / kBK2;
+        const long long k = k0 + kk;
+        const int n = n0 + nn;
+        rb[e] = (k < k_end && n < sh.N) ? fb(k, n) : 0.f;
+      }
+    }
+  };
+  auto stash = [&](int buf) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int idx = tid + e * 256;
+      As[buf][kAKFast ? idx % kBK2 : idx / kT2][kAKFast ? idx / kBK2 : idx % kT2] = ra[e];
+      Bs[buf][kBNFast ? idx / kT2 : idx % kBK2][kBNFast ? idx % kT2 : idx / kBK2] = rb[e];
+    }
+  };
+  int buf = 0;
+  if (k_begin < k_end) {
+    fetch(k_begin);
+    stash(0);
+  }
+  __syncthreads();
+  for (long long k0 = k_begin; k0 < k_end; k0 += kBK2) {
+    const bool more = k0 + kBK2 < k_end;
+    if (more) fetch(k0 + kBK2);                       // global loads in flight under the FMAs below
+#pragma unroll
+    for (int kk = 0; kk < kBK2; ++kk) {
+      const float4 a0 = *reinterpret_cast<const float4*>(&As[buf][kk][ty * 4]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&As[buf][kk][64 + ty * 4]);
+      const float4 b0 = *reinterpret_cast<const float4*>(&Bs[buf][kk][tx * 4]);
+      const float4 b1 = *reinterpret_cast<const float4*>(&Bs[buf][kk][64 + tx * 4]);
+      const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    if (more) {
+      stash(buf ^ 1);                                 // the other buffer: its last readers passed the previous barrier
+      __syncthreads();
+      buf ^= 1;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const long long m = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
+      const int n = n0 + (j < 4 ? tx * 4 + j : 64 + tx * 4 + (j - 4));
+      if (m < sh.M && n < sh.N) fc(m, n, acc[i][j]);
+    }
+}
+
 // [X (rows x k_x, ld ldx) | IN (rows x k_in, ld ldin, column offset folded into the pointer)]
 struct ConcatA {
   const float* x; int ldx, k_x; const float* in; int ldin;

@@ -50,14 +50,25 @@ TapeLayout tape_layout(const nfb::FieldProgram& p, long long rows) {
   return t;
 }
 
-template <class FA, class FB, class FC>
+// Rows per split of a weight-gradient GEMM (reduction over the rows of the batch; the partial tiles are
+// atomicAdd-ed): 2048 rows per split keep ~1,000 CTAs in flight per layer of a 6,144-ray chunk (8192 measured 3x
+// slower: too few CTAs to hide the operand loads).
+constexpr long long kDwSplit = 2048;
+// kAKFast / kBNFast: see sgemm128_kernel (which functor index is contiguous in memory).
+template <bool kAKFast = true, bool kBNFast = true, class FA, class FB, class FC>
 int launch_gemm(nfb_handle* h, long long M, int N, long long K, FA fa, FB fb, FC fc, long long k_split,
                 cudaStream_t s, const char* what) {
   if (M <= 0 || N <= 0 || K <= 0) return 0;
   const long long per = k_split > 0 ? k_split : K;
+#ifdef NFB_TRAIN_SGEMM64
   dim3 grid((unsigned)((M + nfb::train::kTile - 1) / nfb::train::kTile),
             (unsigned)((N + nfb::train::kTile - 1) / nfb::train::kTile), (unsigned)((K + per - 1) / per));
   nfb::train::sgemm_kernel<<<grid, 256, 0, s>>>(nfb::train::GemmShape{M, N, K}, fa, fb, fc, per);
+#else
+  dim3 grid((unsigned)((M + nfb::train::kT2 - 1) / nfb::train::kT2),
+            (unsigned)((N + nfb::train::kT2 - 1) / nfb::train::kT2), (unsigned)((K + per - 1) / per));
+  nfb::train::sgemm128_kernel<kAKFast, kBNFast><<<grid, 256, 0, s>>>(nfb::train::GemmShape{M, N, K}, fa, fb, fc, per);
+#endif
   return launch_check(h, what);
 }
 
@@ -90,8 +101,8 @@ int net_backward(nfb_handle* h, const Net& net, const float* in, float* d_in, in
     const int ldx = producer[i] >= 0 ? net.steps[producer[i]].npad : ld_in;
     nfb::train::ConcatA a{x, ldx, st.k_x, in + st.in_off, ld_in};
     // dW += [X | IN]^T dZ   (reduction over the rows, split)
-    if (launch_gemm(h, K, st.n, rows, nfb::train::ConcatAT{a}, nfb::train::DZB{dz},
-                    nfb::train::AtomicAdd{h->d_gpacked + st.w_off, st.npad}, 2048, s, "sgemm (dW)")) return -1;
+    if (launch_gemm<false, true>(h, K, st.n, rows, nfb::train::ConcatAT{a}, nfb::train::DZB{dz},
+                                 nfb::train::AtomicAdd{h->d_gpacked + st.w_off, st.npad}, kDwSplit, s, "sgemm (dW)")) return -1;
     // db += colsum(dZ)
     {
       dim3 grid((unsigned)((st.n + 31) / 32), (unsigned)std::min<long long>((rows + 255) / 256, 128));
@@ -101,8 +112,8 @@ int net_backward(nfb_handle* h, const Net& net, const float* in, float* d_in, in
     // dX, dIN += dZ W^T
     float* dx = producer[i] >= 0 ? arena + d_out_off[producer[i]] : d_in;
     nfb::train::AccumSplit acc{dx, ldx, st.k_x, d_in + st.in_off, ld_in};
-    if (launch_gemm(h, rows, K, st.n, dz, nfb::train::WeightBT{h->d_packed + st.w_off, st.npad}, acc, 0, s,
-                    "sgemm (dX)")) return -1;
+    if (launch_gemm<true, false>(h, rows, K, st.n, dz, nfb::train::WeightBT{h->d_packed + st.w_off, st.npad}, acc, 0, s,
+                                 "sgemm (dX)")) return -1;
   }
   return 0;
 }
@@ -171,13 +182,13 @@ int tnet_backward(nfb_handle* h, const Net& net, const float* tin, float* d_tin,
     const float* x = producer[i] >= 0 ? tarena + out_t[producer[i]] : tin;
     const int ldx = producer[i] >= 0 ? net.steps[producer[i]].npad : ld_in;
     nfb::train::ConcatA a{x, ldx, st.k_x, tin + st.in_off, ld_in};
-    if (launch_gemm(h, K, st.n, trows, nfb::train::ConcatAT{a}, nfb::train::DZTB{dz},
-                    nfb::train::AtomicAdd{h->d_gpacked + st.w_off, st.npad}, 2048, s, "sgemm (tangent dW)")) return -1;
+    if (launch_gemm<false, true>(h, K, st.n, trows, nfb::train::ConcatAT{a}, nfb::train::DZTB{dz},
+                                 nfb::train::AtomicAdd{h->d_gpacked + st.w_off, st.npad}, kDwSplit, s, "sgemm (tangent dW)")) return -1;
     if (i == 0 && st.k_x == 0) break;             // nothing upstream of the encoded input carries a parameter
     float* dx = producer[i] >= 0 ? tarena + d_out_t[producer[i]] : d_tin;
     nfb::train::AccumSplit acc{dx, ldx, st.k_x, d_tin + st.in_off, ld_in};
-    if (launch_gemm(h, trows, K, st.n, dz, nfb::train::WeightBT{h->d_packed + st.w_off, st.npad}, acc, 0, s,
-                    "sgemm (tangent dX)")) return -1;
+    if (launch_gemm<true, false>(h, trows, K, st.n, dz, nfb::train::WeightBT{h->d_packed + st.w_off, st.npad}, acc, 0, s,
+                                 "sgemm (tangent dX)")) return -1;
   }
   return 0;
 }

@@ -32,7 +32,15 @@
 // w + 4 share a TMEM lane quarter and split a chunk's columns), warp 8 issues the
 // MMAs, warp 9 streams the weights (cp.async.bulk, [W_hi | W_lo] per K-block and
 // chunk), warps 10-11 complete the control warpgroup (setmaxnreg 40 / 232).
-// One issuer "unit" = one K-block of one chunk = 12 MMAs = one ring slot.
+// One issuer "unit" = one K-block of one chunk = 12 MMAs = one ring slot (K-step-major:
+// x_hi W_hi with the A collector filled, x_hi W_lo on the collected operand, x_lo W_hi).
+// Units of a 256-wide layer are issued in the balanced phase order of x3_unit_order
+// (field_tc.cuh); biases reach the epilogue through L1, not the constant bank.
+// Measured (profiles/r02_*): 112.8 K cycles per 128-row tile against a 64.2 K tensor-pipe
+// floor, tensor pipe active 64.6 %, and the whole chip at its 1000 W power limit
+// (~1.72 GHz of 1.965): 0.86 of the power-limited tensor rate in executed FLOPs.
+// Build options for A/B timing: NFB_X3_OPT (epilogue scheduling bits), NFB_X3_CLUSTER,
+// NFB_X3_NO_COLLECT, NFB_X3_ORDER_OLD, NFB_X3_WARP_ARRIVE, NFB_X3_EXP_* (tools/ab_x3.sh).
 #pragma once
 #include <cuda_fp16.h>
 

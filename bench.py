@@ -971,7 +971,7 @@ def run_b200(args):
             'dtype': DTYPE_NAMES[name], 'roofline_frac': roofline(r, wl, B, peaks, name)['frac'],
             'fine_kernel_ms': r['field_ms'][1], 'clocks': r['clocks'],
             'parity': r.get('parity')}
-  if not args.no_cpu_baseline:
+  if not args.no_cpu_baseline and world == 1:      # rank 0 at N = 1 only (task contract)
     line['cpu_baseline'] = cpu_baseline(args.cpu_seconds, args.workload)
   bad = 'parity' in line and not line['parity']['ok']
   if bad:

@@ -51,9 +51,16 @@ TapeLayout tape_layout(const nfb::FieldProgram& p, long long rows) {
 }
 
 // Rows per split of a weight-gradient GEMM (reduction over the rows of the batch; the partial tiles are
-// atomicAdd-ed): 2048 rows per split keep ~1,000 CTAs in flight per layer of a 6,144-ray chunk (8192 measured 3x
-// slower: too few CTAs to hide the operand loads).
-constexpr long long kDwSplit = 2048;
+// atomicAdd-ed).  The output is tiny (<= 3 x 2 tiles of 128 x 128), so the split count sets the parallelism:
+// aim at ~4 CTAs per resident slot (2 per SM) whatever the layer's width; a fixed 2048 rows left a 128-wide
+// layer of a 131,072-row chunk with 64 CTAs for 148 SMs, 8192 rows measured 3x slower.
+inline long long dw_split(const nfb_handle* h, long long M, int N, long long K) {
+  const long long tiles = ((M + nfb::train::kT2 - 1) / nfb::train::kT2) * ((N + nfb::train::kT2 - 1) / nfb::train::kT2);
+  const long long want = std::max<long long>(1, (8LL * h->sm_count) / tiles);   // splits
+  long long per = (K + want - 1) / want;
+  per = (per + 7) / 8 * 8;
+  return std::min<long long>(4096, std::max<long long>(256, per));
+}
 // kAKFast / kBNFast: see sgemm128_kernel (which functor index is contiguous in memory).
 template <bool kAKFast = true, bool kBNFast = true, class FA, class FB, class FC>
 int launch_gemm(nfb_handle* h, long long M, int N, long long K, FA fa, FB fb, FC fc, long long k_split,
@@ -102,7 +109,7 @@ int net_backward(nfb_handle* h, const Net& net, const float* in, float* d_in, in
     nfb::train::ConcatA a{x, ldx, st.k_x, in + st.in_off, ld_in};
     // dW += [X | IN]^T dZ   (reduction over the rows, split)
     if (launch_gemm<false, true>(h, K, st.n, rows, nfb::train::ConcatAT{a}, nfb::train::DZB{dz},
-                                 nfb::train::AtomicAdd{h->d_gpacked + st.w_off, st.npad}, kDwSplit, s, "sgemm (dW)")) return -1;
+                                 nfb::train::AtomicAdd{h->d_gpacked + st.w_off, st.npad}, dw_split(h, K, st.n, rows), s, "sgemm (dW)")) return -1;
     // db += colsum(dZ)
     {
       dim3 grid((unsigned)((st.n + 31) / 32), (unsigned)std::min<long long>((rows + 255) / 256, 128));
@@ -183,7 +190,7 @@ int tnet_backward(nfb_handle* h, const Net& net, const float* tin, float* d_tin,
     const int ldx = producer[i] >= 0 ? net.steps[producer[i]].npad : ld_in;
     nfb::train::ConcatA a{x, ldx, st.k_x, tin + st.in_off, ld_in};
     if (launch_gemm<false, true>(h, K, st.n, trows, nfb::train::ConcatAT{a}, nfb::train::DZTB{dz},
-                                 nfb::train::AtomicAdd{h->d_gpacked + st.w_off, st.npad}, kDwSplit, s, "sgemm (tangent dW)")) return -1;
+                                 nfb::train::AtomicAdd{h->d_gpacked + st.w_off, st.npad}, dw_split(h, K, st.n, trows), s, "sgemm (tangent dW)")) return -1;
     if (i == 0 && st.k_x == 0) break;             // nothing upstream of the encoded input carries a parameter
     float* dx = producer[i] >= 0 ? tarena + d_out_t[producer[i]] : d_tin;
     nfb::train::AccumSplit acc{dx, ldx, st.k_x, d_tin + st.in_off, ld_in};
